@@ -1,0 +1,105 @@
+/*
+ * libspyb200 -- C ABI of the B200-native per-trial spectral / cross-spectral engine that
+ * stands in for the NumPy/SciPy bodies behind Syncopy's `computeFunction`s.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; 0 = default);
+ *   - return value 0 = ok, non-zero = error, text via spyb_last_error() (thread local);
+ *   - trials are C-contiguous [trial][sample][channel] float32 (AnalogData default dimord,
+ *     reference syncopy/datatype/continuous_data.py:405); complex64 is interleaved (re, im);
+ *   - `out_kind` follows syncopy/shared/const_def.py:25-40:
+ *       0 pow, 1 abs, 2 fourier/complex, 3 real, 4 imag, 5 angle, 6 absreal, 7 absimag.
+ *
+ * The reference has no FFI (it is pure Python); the interface each entry point replaces is
+ * the NumPy-level function cited next to it.  INTEGRATION.md shows the ctypes binding and the
+ * `computeFunction` shim a Syncopy maintainer would add.
+ */
+#ifndef SPYB200_H
+#define SPYB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPYB_VERSION 100
+
+/* library / device management ---------------------------------------------------------- */
+int spyb_version(void);
+int spyb_init(int device);                 /* cudaSetDevice + warm-up of the context       */
+const char* spyb_last_error(void);
+long long spyb_launch_count(void);         /* number of kernels this library has launched  */
+int spyb_max_fft_len(int pow2);            /* largest supported length (pow2 / arbitrary)  */
+
+/*
+ * (Multi-)tapered FFT of whole trials.
+ * Replaces: syncopy/specest/mtmfft.py:16-129 (`mtmfft`), plus the arithmetic of
+ *           syncopy/specest/compRoutines.py:169-189 (`mtmfft_cF`: detrend, frequency gather,
+ *           spectralConversions, taper mean).
+ *   x            [n_trials][n_samples][n_chan] float32, `trial_stride` elements between trials
+ *   tapers       [n_tapers][n_samples] float32, already normalised (_norm_spec.py:27-46)
+ *   nfft         padded length (`nSamples` of the reference), any length >= n_samples
+ *   scale        sqrt(2) / norm of `_norm_spec` (_norm_spec.py:22, mtmfft.py:119-127)
+ *   polyremoval  -1 none, 0 de-mean, 1 linear detrend (scipy.signal.detrend over the trial)
+ *   demean_taper subtract the mean of each tapered series (mtmfft.py:114-116)
+ *   freq_idx     optional gather list into the nfft/2+1 bins (best_match, compRoutines.py:158)
+ *   keeptapers   0: average the converted output over tapers (compRoutines.py:188-189)
+ *   out          element (trial, taper, fi, chan) at trial*so_trial + taper*so_taper + fi*so_freq + chan;
+ *                float32 or complex64 depending on out_kind
+ *   chan_amax    optional [n_chan] float32, atomically max-updated with max(|re|,|im|)
+ */
+int spyb_mtmfft(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan,
+                const float* tapers, int n_tapers, int nfft, float scale,
+                int polyremoval, int demean_taper,
+                const int* freq_idx, int n_freq_out, int out_kind, int keeptapers,
+                void* out, long long so_trial, long long so_taper, long long so_freq,
+                float* chan_amax, void* stream);
+
+/*
+ * (Multi-)tapered short-time FFT on sliding frames, no frames are materialised.
+ * Replaces: syncopy/specest/stft.py:16-159 and syncopy/specest/mtmconvol.py:17-152.
+ *   frame f covers samples [frame_start0 + f*hop, +nperseg) of the trial; samples outside
+ *   [0, n_samples) read as zero (boundary='zeros' -> frame_start0 = -nperseg/2; the end padding
+ *   of stft.py:112-117 is implied).  Per-segment detrending includes those zeros
+ *   (stft.py:131-132).  tapers [n_tapers][nperseg]; scale = sqrt(2)/nperseg (stft.py:154).
+ *   out element (trial, frame, taper, fi, chan) at
+ *       trial*so_trial + frame*so_frame + taper*so_taper + fi*so_freq + chan.
+ */
+int spyb_mtmconvol(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan,
+                   const float* tapers, int n_tapers, int nperseg, int hop, int frame_start0, int n_frames,
+                   float scale, int polyremoval,
+                   const int* freq_idx, int n_freq_out, int out_kind, int keeptapers,
+                   void* out, long long so_trial, long long so_frame, long long so_taper, long long so_freq,
+                   void* stream);
+
+/*
+ * Cross-spectral contraction:  acc[f][i][j] = beta*acc[f][i][j]
+ *                                 + alpha * sum_{r < n_rows} X[f][r][si(i)] * conj(X[f][r][sj(j)])
+ * Replaces: syncopy/connectivity/csd.py:98-102 (outer product + taper mean),
+ *           syncopy/connectivity/ST_compRoutines.py:84-116 (`spectral_dyadic_product_cF`) and, when the
+ *           rows of many trials are passed at once, the trial sum of
+ *           syncopy/shared/computational_routine.py:1022-1025.
+ *   spectra  complex64, element (f, r, c) at f*sx_f + r*sx_r + c   (r = trial*n_tapers + taper)
+ *   idx_i/j  optional channel subsets (send_idx / rec_idx); NULL = all channels (Hermitian result)
+ *   acc      complex64 [n_freq][Ci][Cj]
+ *   impl     0 auto, 1 CUDA-core FP32 kernel, 2 tcgen05 tensor-core kernel (errors if not applicable)
+ */
+int spyb_csd_accumulate(const void* spectra, long long sx_f, long long sx_r, int n_rows, int n_freq, int n_chan,
+                        const int* idx_i, int n_i, const int* idx_j, int n_j,
+                        float alpha, float beta, void* acc, int impl, void* stream);
+
+/*
+ * Coherency + output conversion:  out = conv( pre*C_ij / sqrt(pre*C_ii * pre*C_jj) ).
+ * Replaces: syncopy/connectivity/csd.py:118-172 (`normalize_csd`).
+ *   csd [n_mat][n_chan][n_chan] complex64; out float32 or complex64 of the same shape.
+ */
+int spyb_csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind,
+                       void* out, void* stream);
+
+/* x *= s on n float32 (trial mean `/= nTrials`, computational_routine.py:1030-1032) */
+int spyb_scale(float* x, long long n, float s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPYB200_H */

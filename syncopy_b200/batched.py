@@ -1,0 +1,187 @@
+"""
+Whole-dataset ("batched") entry points: all trials of an `AnalogData`-like
+array move through the GPU in one go instead of one `computeFunction` call per
+trial.  This is the throughput path behind a `compute_sequential` override
+(INTEGRATION.md); results are laid out exactly as the
+reference's runtime would stack the per-trial results (trial k -> row block k).
+
+Inputs are `[nTrials, nSamples, nChannels]` float32, either host `ndarray`s
+(copied through pinned memory) or CUDA tensors.  Outputs are CUDA tensors
+unless `to_host=True`.
+"""
+import numpy as np
+import torch
+
+from . import hostmath as hm
+from .engine import get_engine
+
+# upper bound for the intermediate spectra buffer of the cross-spectral path
+MAX_SPECTRA_BYTES = 24 << 30
+
+
+def _device_trials(eng, trials):
+    if isinstance(trials, torch.Tensor):
+        assert trials.dim() == 3
+        return trials.to(device=eng.tdev, dtype=torch.float32).contiguous()
+    arr = np.ascontiguousarray(trials, dtype=np.float32)
+    assert arr.ndim == 3, "trials must be [nTrials, nSamples, nChannels]"
+    return torch.from_numpy(arr).to(eng.tdev, non_blocking=True)
+
+
+def _freq_selection(nfft, samplerate, foi):
+    freqs = np.fft.rfftfreq(nfft, 1 / samplerate)
+    if foi is None:
+        return freqs, None
+    sel, idx = hm.best_match(freqs, foi, squash_duplicates=True)
+    if idx.size == freqs.size and np.array_equal(idx, np.arange(freqs.size)):
+        return freqs, None
+    return sel, idx
+
+
+def mtmfft(trials, samplerate, nSamples=None, taper="hann", taper_opt=None, demean_taper=False,
+           ft_compat=False, foi=None, polyremoval=None, output="pow", keeptapers=True,
+           keeptrials=True, to_host=False, engine=None):
+    """
+    All-trials version of `mtmfft_cF` (syncopy/specest/compRoutines.py:59-191).
+    Returns (spec [nTrials | 1, nTaperOut, nFreq, nChannels], freqs).
+    """
+    eng = engine or get_engine()
+    x = _device_trials(eng, trials)
+    B, n_sig, _ = x.shape
+    nfft = n_sig if nSamples is None else int(nSamples)
+    freqs, fidx = _freq_selection(nfft, samplerate, foi)
+    tapers = eng.taper_table(taper, n_sig, nfft, taper_opt)
+    spec = eng.mtmfft(x, tapers, nfft, hm.mtmfft_scale(n_sig, nfft, ft_compat),
+                      polyremoval=hm.polyremoval_code(polyremoval), demean_taper=demean_taper,
+                      freq_idx=fidx, output=output, keeptapers=keeptapers)
+    if not keeptrials:
+        # runtime's trial mean: sum of the per-trial results / nTrials (computational_routine.py:1022-1032)
+        spec = spec.sum(dim=0, keepdim=True) / B
+    if to_host:
+        spec = spec.cpu().numpy()
+    return spec, freqs
+
+
+def mtmconvol(trials, samplerate, nperseg, noverlap, taper="hann", taper_opt=None, boundary="zeros",
+              padded=True, foi=None, polyremoval=0, output="pow", keeptapers=True, to_host=False,
+              engine=None):
+    """
+    All-trials version of the equidistant branch of `mtmconvol_cF`
+    (syncopy/specest/compRoutines.py:386-390,410-413) for `soi = postselect = slice(None)`.
+    Returns (spec [nTrials, nTime, nTaperOut, nFreq, nChannels], freqs).
+    """
+    eng = engine or get_engine()
+    x = _device_trials(eng, trials)
+    _, n_sig, _ = x.shape
+    hop = nperseg - noverlap
+    freqs, fidx = _freq_selection(nperseg, samplerate, foi)
+    tapers = eng.taper_table(taper, nperseg, nperseg, taper_opt, periodic_dpss=True)
+    n_keep = int(np.ceil(n_sig / hop))
+    ext = n_sig
+    if boundary is not None:
+        frame_start0 = -(nperseg // 2)
+        ext += 2 * (nperseg // 2)
+    else:
+        frame_start0 = 0
+        n_keep -= nperseg
+    if padded:
+        ext += (-(ext - nperseg) % hop) % nperseg
+    n_frames = max(0, min(n_keep, (ext - noverlap) // hop))
+    spec = eng.mtmconvol(x, tapers, nperseg, hop, frame_start0, n_frames, hm.stft_scale(nperseg),
+                         polyremoval=hm.polyremoval_code(polyremoval), freq_idx=fidx, output=output,
+                         keeptapers=keeptapers)
+    if to_host:
+        spec = spec.cpu().numpy()
+    return spec, freqs
+
+
+class CrossSpectraSum:
+    """Trial-SUMMED cross spectra of one rank: `csd_sum / n_trials` is the trial average."""
+
+    def __init__(self, csd_sum, n_trials, freqs):
+        self.csd_sum, self.n_trials, self.freqs = csd_sum, n_trials, freqs
+
+    def average(self, engine=None):
+        eng = engine or get_engine()
+        return eng.scale_(self.csd_sum.clone(), 1.0 / self.n_trials)[None]
+
+
+def cross_spectra_sum(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_opt=None,
+                      demean_taper=False, polyremoval=False, engine=None, impl=0, out=None):
+    """
+    Sum over trials of the single-trial cross spectra of `cross_spectra_cF`
+    (syncopy/connectivity/ST_compRoutines.py:268-424), i.e. what the runtime accumulates for
+    `keeptrials=False` before dividing by nTrials.  Two kernels per trial chunk: the tapered FFT
+    writes frequency-major spectra [nFreq][trial*taper][channel]; the contraction reduces them to
+    [nFreq][channel][channel] in one pass over all (trial, taper) rows.
+    """
+    eng = engine or get_engine()
+    x = _device_trials(eng, trials)
+    B, n_sig, n_chan = x.shape
+    nfft = n_sig if nSamples is None else int(nSamples)
+    freqs, fidx = _freq_selection(nfft, samplerate, foi)
+    n_freq = freqs.size
+    tapers = eng.taper_table(taper, n_sig, nfft, taper_opt)
+    K = tapers.shape[0]
+    scale = hm.mtmfft_scale(n_sig, nfft)
+    pr = hm.polyremoval_code(polyremoval)
+
+    bytes_per_trial = n_freq * K * n_chan * 8
+    chunk = max(1, min(B, MAX_SPECTRA_BYTES // max(1, bytes_per_trial)))
+    acc = out
+    spectra = torch.empty((n_freq, min(chunk, B) * K, n_chan), dtype=torch.complex64, device=eng.tdev)
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        view = spectra[:, :nb * K, :]
+        eng.mtmfft(x[b0:b0 + nb], tapers, nfft, scale, polyremoval=pr, demean_taper=demean_taper,
+                   freq_idx=fidx, output="fourier", keeptapers=True, out=view, freq_major=True)
+        acc = eng.csd_accumulate(view, acc=acc, alpha=1.0 / K, beta=0.0 if (b0 == 0 and out is None) else 1.0,
+                                 impl=impl)
+    return CrossSpectraSum(acc, B, freqs)
+
+
+def cross_spectra(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_opt=None,
+                  demean_taper=False, polyremoval=False, keeptrials=False, to_host=False, engine=None,
+                  impl=0):
+    """
+    `CrossSpectra` compute routine over all trials.  keeptrials=False returns the trial average
+    [1, nFreq, C, C]; keeptrials=True stacks the single-trial results [nTrials, nFreq, C, C].
+    """
+    eng = engine or get_engine()
+    if not keeptrials:
+        res = cross_spectra_sum(trials, samplerate, nSamples, foi, taper, taper_opt, demean_taper,
+                                polyremoval, engine=eng, impl=impl)
+        csd, freqs = res.average(eng), res.freqs
+    else:
+        x = _device_trials(eng, trials)
+        B, n_sig, n_chan = x.shape
+        nfft = n_sig if nSamples is None else int(nSamples)
+        freqs, fidx = _freq_selection(nfft, samplerate, foi)
+        tapers = eng.taper_table(taper, n_sig, nfft, taper_opt)
+        K = tapers.shape[0]
+        csd = torch.empty((B, freqs.size, n_chan, n_chan), dtype=torch.complex64, device=eng.tdev)
+        for b in range(B):
+            spectra = eng.mtmfft(x[b:b + 1], tapers, nfft, hm.mtmfft_scale(n_sig, nfft),
+                                 polyremoval=hm.polyremoval_code(polyremoval), demean_taper=demean_taper,
+                                 freq_idx=fidx, output="fourier", keeptapers=True, freq_major=True)
+            eng.csd_accumulate(spectra, acc=csd[b], alpha=1.0 / K, beta=0.0, impl=impl)
+    if to_host:
+        csd = csd.cpu().numpy()
+    return csd, freqs
+
+
+def coherence(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_opt=None,
+              polyremoval=0, output="abs", to_host=False, engine=None, impl=0):
+    """
+    `connectivityanalysis(method='coh')` compute chain: CrossSpectra(keeptrials=False) followed by
+    NormalizeCrossSpectra (syncopy/connectivity/connectivity_analysis.py:460-473,549,587-599,677-679).
+    The 1/nTrials of the trial mean is folded into the normalisation kernel.
+    Returns (coh [1, nFreq, C, C], freqs).
+    """
+    eng = engine or get_engine()
+    res = cross_spectra_sum(trials, samplerate, nSamples, foi, taper, taper_opt, False, polyremoval,
+                            engine=eng, impl=impl)
+    coh = eng.csd_normalize(res.csd_sum[None], output=output, pre_scale=1.0 / res.n_trials)
+    if to_host:
+        coh = coh.cpu().numpy()
+    return coh, res.freqs

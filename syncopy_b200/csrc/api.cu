@@ -1,0 +1,108 @@
+// extern "C" surface of libspyb200.so -- see include/spyb200.h for the contract.
+#include "../../include/spyb200.h"
+#include "common.cuh"
+#include "plan.cuh"
+#include "spyb_internal.h"
+
+#include <atomic>
+
+namespace spyb {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace spyb
+
+using namespace spyb;
+
+extern "C" {
+
+int spyb_version(void) { return SPYB_VERSION; }
+
+const char* spyb_last_error(void) { return err_buf(); }
+
+long long spyb_launch_count(void) { return g_launches.load(); }
+
+int spyb_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail("no CUDA device available (%s)", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail("device %d out of range (have %d)", device, n);
+    SPYB_CUDA(cudaSetDevice(device));
+    SPYB_CUDA(cudaFree(0));
+    cudaDeviceProp prop;
+    SPYB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail("libspyb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    return 0;
+}
+
+int spyb_max_fft_len(int pow2) { return pow2 ? 16384 : 8192; }
+
+int spyb_mtmfft(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan,
+                const float* tapers, int n_tapers, int nfft, float scale,
+                int polyremoval, int demean_taper,
+                const int* freq_idx, int n_freq_out, int out_kind, int keeptapers,
+                void* out, long long so_trial, long long so_taper, long long so_freq,
+                float* chan_amax, void* stream) {
+    if (nfft < n_samples) return fail("nfft (%d) must be >= n_samples (%d)", nfft, n_samples);
+    if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
+    MtmFramesDesc d;
+    d.x = x; d.trial_stride = trial_stride;
+    d.n_trials = n_trials; d.n_samples = n_samples; d.n_chan = n_chan;
+    d.n_win = n_samples; d.n_dft = nfft;
+    d.frame_start0 = 0; d.hop = 1; d.n_frames = 1;
+    d.tapers = tapers; d.n_tapers = n_tapers;
+    d.polyremoval = polyremoval; d.demean_taper = demean_taper; d.scale = scale;
+    d.freq_idx = freq_idx; d.n_freq_out = n_freq_out;
+    d.out_kind = out_kind; d.keeptapers = keeptapers;
+    d.out = out; d.so_trial = so_trial; d.so_frame = 0; d.so_taper = so_taper; d.so_freq = so_freq;
+    d.chan_amax = chan_amax;
+    return mtm_frames(d, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_mtmconvol(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan,
+                   const float* tapers, int n_tapers, int nperseg, int hop, int frame_start0, int n_frames,
+                   float scale, int polyremoval,
+                   const int* freq_idx, int n_freq_out, int out_kind, int keeptapers,
+                   void* out, long long so_trial, long long so_frame, long long so_taper, long long so_freq,
+                   void* stream) {
+    if (nperseg < 1 || hop < 1) return fail("nperseg (%d) and hop (%d) must be positive", nperseg, hop);
+    if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
+    MtmFramesDesc d;
+    d.x = x; d.trial_stride = trial_stride;
+    d.n_trials = n_trials; d.n_samples = n_samples; d.n_chan = n_chan;
+    d.n_win = nperseg; d.n_dft = nperseg;
+    d.frame_start0 = frame_start0; d.hop = hop; d.n_frames = n_frames;
+    d.tapers = tapers; d.n_tapers = n_tapers;
+    d.polyremoval = polyremoval; d.demean_taper = 0; d.scale = scale;
+    d.freq_idx = freq_idx; d.n_freq_out = n_freq_out;
+    d.out_kind = out_kind; d.keeptapers = keeptapers;
+    d.out = out; d.so_trial = so_trial; d.so_frame = so_frame; d.so_taper = so_taper; d.so_freq = so_freq;
+    return mtm_frames(d, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_csd_accumulate(const void* spectra, long long sx_f, long long sx_r, int n_rows, int n_freq, int n_chan,
+                        const int* idx_i, int n_i, const int* idx_j, int n_j,
+                        float alpha, float beta, void* acc, int impl, void* stream) {
+    if ((idx_i == nullptr) != (idx_j == nullptr))
+        return fail("idx_i and idx_j must both be given or both be NULL");
+    CsdDesc d;
+    d.spectra = spectra; d.sx_f = sx_f; d.sx_r = sx_r;
+    d.n_rows = n_rows; d.n_freq = n_freq; d.n_chan = n_chan;
+    d.idx_i = idx_i; d.idx_j = idx_j; d.n_i = n_i; d.n_j = n_j;
+    d.alpha = alpha; d.beta = beta; d.acc = acc;
+    if (impl == 2) return fail("tensor-core CSD kernel not available in this build");
+    return csd_accumulate_simt(d, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind,
+                       void* out, void* stream) {
+    if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
+    return csd_normalize(csd, n_mat, n_chan, pre_scale, out_kind, out, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_scale(float* x, long long n, float s, void* stream) {
+    return scale_inplace(x, n, s, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

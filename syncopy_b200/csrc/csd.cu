@@ -1,0 +1,240 @@
+// K2 (SIMT variant) / K3: cross-spectral contraction and coherency normalisation.
+//
+// K2 replaces the broadcasting outer product + taper mean of
+//   syncopy/connectivity/csd.py:98-102 and ST_compRoutines.py:84-116,
+// and -- when rows of several trials are handed over at once -- the runtime's trial sum
+//   syncopy/shared/computational_routine.py:1022-1032:
+//   acc[f][i][j] = beta * acc[f][i][j] + alpha * sum_r X[f][r][si(i)] * conj(X[f][r][sj(j)])
+// where r runs over (trial, taper) rows.  Per frequency this is a rank-R Hermitian update;
+// this file holds the FP32 CUDA-core version (64x64 tile per block, 4x4 complex per
+// thread), csd_tc.cu the tcgen05 tensor-core version used for large aligned problems.
+//
+// K3 replaces syncopy/connectivity/csd.py:161-170 (coherency) + the output conversion.
+#include "common.cuh"
+#include "spyb_internal.h"
+
+namespace spyb {
+
+constexpr int CSD_T = 64;      // tile edge
+constexpr int CSD_RK = 8;      // rows per stage
+
+struct CsdArgs {
+    const float2* X;           // spectra, element (f, r, c) at f*sx_f + r*sx_r + c
+    long long sx_f, sx_r;
+    int n_rows, n_freq, n_chan;
+    const int* idx_i;          // optional channel subsets (spectral_dyadic_product_cF send/rec)
+    const int* idx_j;
+    int Ci, Cj;
+    int hermitian;             // idx_i == idx_j == null: compute upper tiles, mirror the rest
+    float2* acc;               // [n_freq][Ci][Cj]
+    float alpha, beta;
+};
+
+__global__ void __launch_bounds__(256) csd_simt_kernel(const CsdArgs a) {
+    __shared__ float2 sA[CSD_RK][CSD_T];
+    __shared__ float2 sB[CSD_RK][CSD_T];
+    __shared__ float2 sT[CSD_T][CSD_T + 1];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int f = blockIdx.y;
+
+    // decode tile
+    int ti, tj;
+    const int ntj = (a.Cj + CSD_T - 1) / CSD_T;
+    if (a.hermitian) {
+        int rem = blockIdx.x;
+        ti = 0;
+        while (rem >= ntj - ti) { rem -= ntj - ti; ++ti; }
+        tj = ti + rem;
+    } else {
+        ti = blockIdx.x / ntj;
+        tj = blockIdx.x % ntj;
+    }
+    const int i0 = ti * CSD_T, j0 = tj * CSD_T;
+
+    // operand fetch: thread loads 2 elements of A and 2 of B per stage (8 rows x 64 cols each)
+    const int lc = tid & 63, lr = tid >> 6;      // lr in 0..3 -> rows lr and lr+4
+    int ci = i0 + lc, cj = j0 + lc;
+    const bool ci_ok = ci < a.Ci, cj_ok = cj < a.Cj;
+    if (a.idx_i && ci_ok) ci = a.idx_i[ci];
+    if (a.idx_j && cj_ok) cj = a.idx_j[cj];
+    const float2* __restrict__ Xf = a.X + (long long)f * a.sx_f;
+
+    float2 acc[4][4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = make_float2(0.f, 0.f);
+
+    const float2 zero = make_float2(0.f, 0.f);
+    float2 pa[2], pb[2];
+    auto fetch = [&](int r0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = r0 + lr + 4 * h;
+            const bool ok = r < a.n_rows;
+            pa[h] = (ok && ci_ok) ? __ldg(Xf + (long long)r * a.sx_r + ci) : zero;
+            pb[h] = (ok && cj_ok) ? __ldg(Xf + (long long)r * a.sx_r + cj) : zero;
+        }
+    };
+
+    fetch(0);
+    for (int r0 = 0; r0 < a.n_rows; r0 += CSD_RK) {
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            sA[lr + 4 * h][lc] = pa[h];
+            sB[lr + 4 * h][lc] = pb[h];
+        }
+        __syncthreads();
+        if (r0 + CSD_RK < a.n_rows) fetch(r0 + CSD_RK);
+#pragma unroll
+        for (int r = 0; r < CSD_RK; ++r) {
+            float2 xi[4], xj[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                xi[q] = sA[r][ty + 16 * q];
+                xj[q] = sB[r][tx + 16 * q];
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    // acc += xi * conj(xj)
+                    acc[ii][jj].x = fmaf(xi[ii].x, xj[jj].x, fmaf(xi[ii].y, xj[jj].y, acc[ii][jj].x));
+                    acc[ii][jj].y = fmaf(xi[ii].y, xj[jj].x, fmaf(-xi[ii].x, xj[jj].y, acc[ii][jj].y));
+                }
+        }
+    }
+
+    // ---- epilogue ----
+    // Hermitian mode: every value above (or on) the diagonal is computed once and written twice
+    // (as is, and conjugated into the mirrored position), so the result is exactly Hermitian.
+    float2* __restrict__ out = a.acc + (long long)f * a.Ci * a.Cj;
+    const bool diag_tile = a.hermitian && ti == tj;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        const int i = i0 + ty + 16 * ii;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + tx + 16 * jj;
+            float2 val = make_float2(acc[ii][jj].x * a.alpha, acc[ii][jj].y * a.alpha);
+            if (diag_tile && i == j) val.y = 0.f;           // auto-spectra are exactly real
+            if (a.hermitian) sT[ty + 16 * ii][tx + 16 * jj] = val;
+            if (i < a.Ci && j < a.Cj && (!diag_tile || i <= j)) {
+                float2* o = out + (long long)i * a.Cj + j;
+                if (a.beta != 0.f) { const float2 old = *o; val.x += a.beta * old.x; val.y += a.beta * old.y; }
+                *o = val;
+            }
+        }
+    }
+    if (a.hermitian) {
+        __syncthreads();
+        // mirrored block: out[j][i] = conj(val[i][j]); lanes run along i for coalescing
+        for (int e = tid; e < CSD_T * CSD_T; e += 256) {
+            const int jl = e >> 6, il = e & 63;
+            const int i = i0 + il, j = j0 + jl;
+            if (i < a.Ci && j < a.Cj && (!diag_tile || il < jl)) {
+                float2 val = sT[il][jl];
+                val.y = -val.y;
+                float2* o = out + (long long)j * a.Cj + i;
+                if (a.beta != 0.f) { const float2 old = *o; val.x += a.beta * old.x; val.y += a.beta * old.y; }
+                *o = val;
+            }
+        }
+    }
+}
+
+int csd_accumulate_simt(const CsdDesc& d, cudaStream_t stream) {
+    if (d.n_freq <= 0 || d.n_chan <= 0) return 0;
+    CsdArgs a;
+    a.X = reinterpret_cast<const float2*>(d.spectra);
+    a.sx_f = d.sx_f; a.sx_r = d.sx_r;
+    a.n_rows = d.n_rows; a.n_freq = d.n_freq; a.n_chan = d.n_chan;
+    a.idx_i = d.idx_i; a.idx_j = d.idx_j;
+    a.Ci = d.idx_i ? d.n_i : d.n_chan;
+    a.Cj = d.idx_j ? d.n_j : d.n_chan;
+    a.hermitian = (!d.idx_i && !d.idx_j) ? 1 : 0;
+    a.acc = reinterpret_cast<float2*>(d.acc);
+    a.alpha = d.alpha; a.beta = d.beta;
+    const int nti = (a.Ci + CSD_T - 1) / CSD_T, ntj = (a.Cj + CSD_T - 1) / CSD_T;
+    const int tiles = a.hermitian ? nti * (nti + 1) / 2 : nti * ntj;
+    if (d.n_freq > 65535) return fail("csd: more than 65535 frequencies per launch (%d)", d.n_freq);
+    dim3 grid(tiles, d.n_freq);
+    csd_simt_kernel<<<grid, 256, 0, stream>>>(a);
+    SPYB_LAUNCH_CHECK("csd_simt_kernel");
+    count_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: coherency  C_ij / sqrt(C_ii C_jj)  (+ scale) and output conversion
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 csqrt_principal(float2 z) {
+    const float m = hypotf(z.x, z.y);
+    if (m == 0.f) return make_float2(0.f, z.y);
+    float re = sqrtf(0.5f * (m + fabsf(z.x)));
+    float im = 0.5f * z.y / re;
+    if (z.x >= 0.f) return make_float2(re, im);
+    // z.x < 0: swap roles, keep the sign of the imaginary part
+    return make_float2(fabsf(im), copysignf(re, z.y));
+}
+
+__global__ void __launch_bounds__(256) csd_normalize_kernel(const float2* __restrict__ csd, int n_chan,
+                                                            long long n_mat, float pre_scale, int out_kind,
+                                                            void* __restrict__ out) {
+    // one block per (matrix, row i); threads run along j
+    const long long row = blockIdx.x;
+    const long long mat = row / n_chan;
+    const int i = (int)(row % n_chan);
+    if (mat >= n_mat) return;
+    const float2* __restrict__ M = csd + mat * n_chan * n_chan;
+    float2 dii = M[(long long)i * n_chan + i];
+    dii.x *= pre_scale; dii.y *= pre_scale;
+    for (int j = threadIdx.x; j < n_chan; j += blockDim.x) {
+        float2 djj = M[(long long)j * n_chan + j];
+        djj.x *= pre_scale; djj.y *= pre_scale;
+        float2 cij = M[(long long)i * n_chan + j];
+        cij.x *= pre_scale; cij.y *= pre_scale;
+        const float2 den = csqrt_principal(cmul(dii, djj));
+        // complex division cij / den
+        const float d2 = den.x * den.x + den.y * den.y;
+        const float2 coh = make_float2((cij.x * den.x + cij.y * den.y) / d2, (cij.y * den.x - cij.x * den.y) / d2);
+        const long long o = row * n_chan + j;
+        if (out_kind == OUT_FOURIER) reinterpret_cast<float2*>(out)[o] = coh;
+        else reinterpret_cast<float*>(out)[o] = convert_real(coh, out_kind);
+    }
+}
+
+int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind, void* out,
+                  cudaStream_t stream) {
+    if (n_mat <= 0 || n_chan <= 0) return 0;
+    const long long rows = n_mat * n_chan;
+    if (rows > 2147483647LL) return fail("csd_normalize: too many rows (%lld)", rows);
+    const int threads = n_chan >= 256 ? 256 : (n_chan >= 128 ? 128 : 64);
+    csd_normalize_kernel<<<(unsigned)rows, threads, 0, stream>>>(reinterpret_cast<const float2*>(csd), n_chan,
+                                                                n_mat, pre_scale, out_kind, out);
+    SPYB_LAUNCH_CHECK("csd_normalize_kernel");
+    count_launch();
+    return 0;
+}
+
+// in-place scale of a float buffer (trial mean: computational_routine.py:1030-1032)
+__global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = i0; i < n; i += stride) x[i] *= s;
+}
+
+int scale_inplace(float* x, long long n, float s, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 1023) / 1024;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    scale_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, s);
+    SPYB_LAUNCH_CHECK("scale_kernel");
+    count_launch();
+    return 0;
+}
+
+}  // namespace spyb

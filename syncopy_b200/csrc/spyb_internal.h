@@ -1,0 +1,46 @@
+// Internal interfaces between the translation units of libspyb200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace spyb {
+
+void count_launch();                 // bumps the counter behind spyb_launch_count()
+
+// Generic "tapered real FFT of frames" job; mtmfft is the 1-frame case (see mtm.cu)
+struct MtmFramesDesc {
+    const float* x = nullptr;        // device, [trial][sample][channel]
+    long long trial_stride = 0;
+    int n_trials = 0, n_samples = 0, n_chan = 0;
+    int n_win = 0, n_dft = 0;
+    int frame_start0 = 0, hop = 1, n_frames = 1;
+    const float* tapers = nullptr;   // device, [n_tapers][n_win]
+    int n_tapers = 1;
+    int polyremoval = -1, demean_taper = 0;
+    float scale = 1.f;
+    const int* freq_idx = nullptr;   // device or null
+    int n_freq_out = 0;
+    int out_kind = 0, keeptapers = 1;
+    void* out = nullptr;             // device
+    long long so_trial = 0, so_frame = 0, so_taper = 0, so_freq = 0;
+    float* chan_amax = nullptr;
+};
+int mtm_frames(const MtmFramesDesc& d, cudaStream_t stream);
+
+// Cross-spectral contraction acc = beta*acc + alpha * sum_r X_r X_r^H per frequency (csd.cu)
+struct CsdDesc {
+    const void* spectra = nullptr;   // device complex64, element (f, r, c) at f*sx_f + r*sx_r + c
+    long long sx_f = 0, sx_r = 0;
+    int n_rows = 0, n_freq = 0, n_chan = 0;
+    const int* idx_i = nullptr;      // optional sender / receiver channel subsets (device)
+    const int* idx_j = nullptr;
+    int n_i = 0, n_j = 0;
+    float alpha = 1.f, beta = 0.f;
+    void* acc = nullptr;             // device complex64 [n_freq][Ci][Cj]
+};
+int csd_accumulate_simt(const CsdDesc& d, cudaStream_t stream);
+int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind, void* out,
+                  cudaStream_t stream);
+int scale_inplace(float* x, long long n, float s, cudaStream_t stream);
+
+}  // namespace spyb

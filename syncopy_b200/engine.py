@@ -1,0 +1,185 @@
+"""
+Device-side driver of the per-trial spectral engine.
+
+`Engine` owns nothing but small cached tables (tapers, frequency index lists) on
+one GPU; trial data and results live in caller-provided or freshly allocated
+PyTorch CUDA tensors that are handed to libspyb200 as raw device pointers.
+Everything is enqueued on torch's current stream of the device.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import hostmath as hm
+
+_CDTYPE = {True: torch.complex64, False: torch.float32}
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _trial_layout(x):
+    """Validate a [B, N, C] float32 CUDA stack of dense time-major trials; return the trial stride."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3
+    B, N, Cn = x.shape
+    # (strides of size-1 dimensions are meaningless in torch, so test the 2-D slices instead)
+    assert B == 0 or x[0].is_contiguous(), "trials must be dense [sample][channel]"
+    return x.stride(0) if B > 1 else N * Cn
+
+
+class Engine:
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise _lib.SpybError("no CUDA device visible -- syncopy_b200 has no CPU fallback")
+        self.device = int(device)
+        self.lib = _lib.init(self.device)
+        self.tdev = torch.device("cuda", self.device)
+        self._tables = {}
+
+    # ------------------------------------------------------------------ utilities
+    def stream(self):
+        return torch.cuda.current_stream(self.tdev).cuda_stream
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.tdev)
+
+    def to_device(self, arr, dtype=torch.float32):
+        """Host ndarray / torch tensor -> contiguous CUDA tensor of `dtype` on this device."""
+        if isinstance(arr, torch.Tensor):
+            return arr.to(device=self.tdev, dtype=dtype).contiguous()
+        a = np.ascontiguousarray(arr)
+        return torch.from_numpy(a).to(device=self.tdev, dtype=dtype, non_blocking=False).contiguous()
+
+    def taper_table(self, taper, n_window, n_norm, taper_opt=None, periodic_dpss=False):
+        key = ("taper", taper, int(n_window), int(n_norm), periodic_dpss,
+               tuple(sorted((taper_opt or {}).items())))
+        if key not in self._tables:
+            tab = hm.normalized_tapers(taper, n_window, n_norm, taper_opt, periodic_dpss)
+            self._tables[key] = self.to_device(tab.astype(np.float32))
+        return self._tables[key]
+
+    def index_table(self, idx):
+        if idx is None:
+            return None
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        key = ("idx", idx.tobytes())
+        if key not in self._tables:
+            self._tables[key] = torch.from_numpy(idx).to(self.tdev)
+        return self._tables[key]
+
+    # ------------------------------------------------------------------ K1: mtmfft
+    def mtmfft(self, x, tapers, nfft, scale, polyremoval=-1, demean_taper=False, freq_idx=None,
+               output="fourier", keeptapers=True, out=None, freq_major=False, chan_amax=None):
+        """
+        x [B, N, C] float32 CUDA (trial stride may exceed N*C), tapers [K, N] float32 CUDA.
+        Returns out [B, Kout, nF, C] (default) or, with `freq_major`, [nF, B*Kout, C] -- the
+        layout the cross-spectral contraction consumes.
+        """
+        tstride = _trial_layout(x)
+        B, N, Cn = x.shape
+        K = tapers.shape[0]
+        assert tapers.shape[1] == N and tapers.is_contiguous()
+        kind = hm.out_kind(output)
+        fidx = self.index_table(freq_idx)
+        nF = (nfft // 2 + 1) if fidx is None else fidx.numel()
+        Kout = K if keeptapers else 1
+        dt = _CDTYPE[kind == 2]
+        shape = (nF, B * Kout, Cn) if freq_major else (B, Kout, nF, Cn)
+        if out is None:
+            out = torch.empty(shape, dtype=dt, device=self.tdev)
+        assert out.is_cuda and out.dtype == dt and tuple(out.shape) == shape
+        if freq_major:
+            # `out` may be a row-slice of a larger [nF, R, C] buffer (trial chunks)
+            assert out[0].is_contiguous()
+            so_freq, so_trial, so_taper = (out.stride(0) if nF > 1 else 0), Kout * Cn, Cn
+        else:
+            assert out.is_contiguous()
+            so_trial, so_taper, so_freq = Kout * nF * Cn, nF * Cn, Cn
+        _lib.check(self.lib.spyb_mtmfft(
+            x.data_ptr(), B, tstride, N, Cn, tapers.data_ptr(), K, int(nfft), float(scale),
+            int(polyremoval), int(bool(demean_taper)), _ptr(fidx), nF, kind, int(bool(keeptapers)),
+            out.data_ptr(), so_trial, so_taper, so_freq, _ptr(chan_amax), self.stream()))
+        return out
+
+    # ------------------------------------------------------------------ K4: mtmconvol
+    def mtmconvol(self, x, tapers, nperseg, hop, frame_start0, n_frames, scale, polyremoval=-1,
+                  freq_idx=None, output="fourier", keeptapers=True, out=None):
+        """x [B, N, C] -> out [B, n_frames, Kout, nF, C]."""
+        tstride = _trial_layout(x)
+        B, N, Cn = x.shape
+        K = tapers.shape[0]
+        assert tapers.shape[1] == nperseg and tapers.is_contiguous()
+        kind = hm.out_kind(output)
+        fidx = self.index_table(freq_idx)
+        nF = (nperseg // 2 + 1) if fidx is None else fidx.numel()
+        Kout = K if keeptapers else 1
+        shape = (B, n_frames, Kout, nF, Cn)
+        dt = _CDTYPE[kind == 2]
+        if out is None:
+            out = torch.empty(shape, dtype=dt, device=self.tdev)
+        else:
+            assert out.is_cuda and out.dtype == dt and out.is_contiguous() and out.numel() == int(np.prod(shape))
+        so_freq = Cn
+        so_taper = nF * Cn
+        so_frame = Kout * so_taper
+        so_trial = n_frames * so_frame
+        _lib.check(self.lib.spyb_mtmconvol(
+            x.data_ptr(), B, tstride, N, Cn, tapers.data_ptr(), K, int(nperseg), int(hop),
+            int(frame_start0), int(n_frames), float(scale), int(polyremoval), _ptr(fidx), nF, kind,
+            int(bool(keeptapers)), out.data_ptr(), so_trial, so_frame, so_taper, so_freq, self.stream()))
+        return out
+
+    # ------------------------------------------------------------------ K2 / K3
+    def csd_accumulate(self, spectra, acc=None, alpha=1.0, beta=0.0, idx_i=None, idx_j=None, impl=0):
+        """
+        spectra [nF, R, C] complex64 (rows r = trial*K + taper), acc [nF, Ci, Cj] complex64:
+        acc = beta*acc + alpha * sum_r X_r[si] conj(X_r[sj]).
+        """
+        assert spectra.is_cuda and spectra.dtype == torch.complex64 and spectra.dim() == 3
+        nF, R, Cn = spectra.shape
+        assert spectra[0].is_contiguous()
+        ti, tj = self.index_table(idx_i), self.index_table(idx_j)
+        Ci = Cn if ti is None else ti.numel()
+        Cj = Cn if tj is None else tj.numel()
+        if acc is None:
+            acc = torch.empty((nF, Ci, Cj), dtype=torch.complex64, device=self.tdev)
+            beta = 0.0
+        assert acc.is_contiguous() and acc.shape == (nF, Ci, Cj) and acc.dtype == torch.complex64
+        _lib.check(self.lib.spyb_csd_accumulate(
+            spectra.data_ptr(), (spectra.stride(0) if nF > 1 else 0), Cn, R, nF, Cn,
+            _ptr(ti), Ci, _ptr(tj), Cj, float(alpha), float(beta), acc.data_ptr(), int(impl), self.stream()))
+        return acc
+
+    def csd_normalize(self, csd, output="abs", pre_scale=1.0, out=None):
+        """csd [..., C, C] complex64 -> coherency converted to `output` (same shape)."""
+        assert csd.is_cuda and csd.dtype == torch.complex64 and csd.is_contiguous()
+        Cn = csd.shape[-1]
+        assert csd.shape[-2] == Cn
+        n_mat = csd.numel() // (Cn * Cn)
+        kind = hm.out_kind(output)
+        if out is None:
+            out = torch.empty(csd.shape, dtype=_CDTYPE[kind == 2], device=self.tdev)
+        _lib.check(self.lib.spyb_csd_normalize(csd.data_ptr(), n_mat, Cn, float(pre_scale), kind,
+                                               out.data_ptr(), self.stream()))
+        return out
+
+    def scale_(self, t, s):
+        """In-place t *= s for float32 / complex64 CUDA tensors."""
+        assert t.is_cuda and t.is_contiguous()
+        n = t.numel() * (2 if t.dtype == torch.complex64 else 1)
+        _lib.check(self.lib.spyb_scale(t.data_ptr(), n, float(s), self.stream()))
+        return t
+
+
+_engines = {}
+
+
+def get_engine(device=None):
+    """Process-wide engine per device; the device defaults to LOCAL_RANK / SPYB_DEVICE / 0."""
+    import os
+    if device is None:
+        device = int(os.environ.get("SPYB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

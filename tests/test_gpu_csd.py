@@ -1,0 +1,130 @@
+"""GPU parity of the cross-spectral path (K1 -> K2 -> K3) through the C ABI vs oracle / golden."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, nerr
+from oracle import connectivity as oc
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("name", ["csd_hann_n512", "csd_dpss_n600_pad1024"])
+def test_golden_single_trial_csd(engine, name):
+    from syncopy_b200 import compute_functions as cf
+    z, prm = load_golden(name)
+    kw = prm["kw"]
+    got, meta = cf.cross_spectra_cF(z["x"].copy(), prm["fs"], nSamples=kw.get("nSamples"), taper=kw["taper"],
+                                    taper_opt=kw.get("taper_opt"), demean_taper=kw.get("demean_taper", False),
+                                    polyremoval=None)
+    assert got.shape == (1,) + z["csd"].shape and got.dtype == np.complex64
+    assert nerr(got[0], z["csd"]) <= TOL
+    # Hermitian with exactly real auto-spectra
+    assert np.array_equal(got[0], got[0].conj().transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("n,c,taper,opt", [(256, 1, "hann", None), (300, 3, "hann", None),
+                                           (512, 64, "hann", None), (500, 65, "dpss", {"NW": 3, "Kmax": 5}),
+                                           (1024, 130, "hann", None), (128, 200, "dpss", {"NW": 2, "Kmax": 3})])
+def test_single_trial_vs_oracle(engine, n, c, taper, opt):
+    from syncopy_b200 import compute_functions as cf
+    x = np.random.default_rng(c).normal(size=(n, c)).astype("f4")
+    foi = np.fft.rfftfreq(n, 1e-3)[3:40]
+    got, _ = cf.cross_spectra_cF(x.copy(), 1000., foi=foi, taper=taper, taper_opt=opt, demean_taper=True)
+    want, _ = oc.cross_spectra_cF(x.copy(), 1000., foi=foi, taper=taper, taper_opt=opt, demean_taper=True)
+    assert got.shape == want.shape
+    assert nerr(got, want) <= TOL
+
+
+def test_golden_coherence_chain(engine):
+    """12 trials -> trial-averaged CSD -> coherence, against the real reference's outputs."""
+    from syncopy_b200 import batched
+    z, prm = load_golden("coherence_12trials")
+    csd, freqs = batched.cross_spectra(z["x"], prm["fs"], taper=prm["taper"], polyremoval=None, to_host=True)
+    assert csd.shape == (1,) + z["csd_av"].shape
+    assert nerr(csd[0], z["csd_av"]) <= TOL
+    for output in ("abs", "pow", "fourier", "imag", "real"):
+        coh, _ = batched.coherence(z["x"], prm["fs"], taper=prm["taper"], polyremoval=None, output=output,
+                                   to_host=True)
+        assert coh.dtype == z["coh_" + output].dtype
+        assert nerr(coh, z["coh_" + output]) <= 2 * TOL
+
+
+def test_normalize_cf_all_outputs(engine):
+    from syncopy_b200 import compute_functions as cf
+    z, _ = load_golden("coherence_12trials")
+    for output in ("abs", "pow", "fourier", "complex", "angle", "imag", "real", "absreal", "absimag"):
+        got = cf.normalize_csd_cF(z["csd_av"][None], output)
+        want = oc.normalize_csd_cF(z["csd_av"][None], output)
+        assert got.dtype == want.dtype and got.shape == want.shape
+        if output == "angle":
+            d = np.angle(np.exp(1j * (got.astype(np.float64) - want)))
+            assert np.max(np.abs(d) * np.abs(oc.normalize_csd(z["csd_av"][None], "abs"))) <= 1e-5
+        else:
+            assert nerr(got, want) <= TOL
+
+
+def test_dyadic_product_cf(engine):
+    from syncopy_b200 import compute_functions as cf
+    rng = np.random.default_rng(2)
+    specs = (rng.normal(size=(4, 3, 20, 7)) + 1j * rng.normal(size=(4, 3, 20, 7))).astype(np.complex64)
+    got = cf.spectral_dyadic_product_cF(specs)
+    want = oc.spectral_dyadic_product_cF(specs)
+    assert got.shape == want.shape and nerr(got, want) <= TOL
+    send, rec = [0, 2, 5], [1, 6]
+    got = cf.spectral_dyadic_product_cF(specs, send, 3, rec, 2)
+    want = oc.spectral_dyadic_product_cF(specs, send, 3, rec, 2)
+    assert got.shape == want.shape == (4, 20, 3, 2) and nerr(got, want) <= TOL
+
+
+def test_batched_equals_per_trial_sum(engine):
+    """Trial sharding invariant: CSD sum over all trials == sum of CSD sums over disjoint shards."""
+    from syncopy_b200 import batched
+    trials = synth.white_noise(9, 256, 12)
+    full = batched.cross_spectra_sum(trials, 500., taper="dpss", taper_opt={"NW": 2, "Kmax": 3}, polyremoval=0)
+    a = batched.cross_spectra_sum(trials[:4], 500., taper="dpss", taper_opt={"NW": 2, "Kmax": 3}, polyremoval=0)
+    b = batched.cross_spectra_sum(trials[4:], 500., taper="dpss", taper_opt={"NW": 2, "Kmax": 3}, polyremoval=0)
+    s = (a.csd_sum + b.csd_sum).cpu().numpy()
+    assert nerr(full.csd_sum.cpu().numpy(), s) <= 2e-6
+    want = oc.trial_average([oc.cross_spectra_cF(t.copy(), 500., taper="dpss", taper_opt={"NW": 2, "Kmax": 3},
+                                                 polyremoval=0)[0] for t in trials])
+    assert nerr(full.average().cpu().numpy(), want) <= TOL
+    kept, _ = batched.cross_spectra(trials[:3], 500., taper="hann", keeptrials=True, to_host=True)
+    for k in range(3):
+        one = oc.cross_spectra_cF(trials[k].copy(), 500., taper="hann")[0]
+        assert nerr(kept[k:k + 1], one) <= TOL
+
+
+def test_reference_coherence_property(engine):
+    """tests/backend/test_conn.py:15-85 on the GPU path: 40 Hz coherence peak between shifted harmonics."""
+    from syncopy_b200 import batched
+    rng = np.random.default_rng(synth.TEST_SEED)
+    n, fs, f = 1001, 1000, 40
+    t = np.arange(n) / fs
+    shifts = np.array([0, np.pi / 2, np.pi])
+    trials = np.stack([np.array([np.cos(f * 2 * np.pi * t + ps) for ps in shifts]).T
+                       + rng.standard_normal((n, 3)) for _ in range(100)]).astype("f4")
+    coh, freqs = batched.coherence(trials, fs, taper="hann", polyremoval=None, to_host=True)
+    c01 = coh[0, :, 0, 1]
+    k = np.argmax(c01)
+    assert f - 5 < freqs[k] < f + 5 and 0.9 < c01[k] < 1
+    assert np.all(c01[:k - 2] < 0.4) and np.all(c01[k + 2:] < 0.4)
+
+
+def test_cfg2_shape_properties(engine):
+    """BASELINE cfg-2 shape (256 ch x 4096 smp), 8 trials: Hermitian, PSD diagonal, shard additivity."""
+    from syncopy_b200 import batched
+    trials = synth.white_noise(8, 4096, 256)
+    res = batched.cross_spectra_sum(trials, 1000., taper="hann", polyremoval=0)
+    S = res.csd_sum
+    assert S.shape == (2049, 256, 256)
+    assert (S - S.conj().transpose(1, 2)).abs().max().item() == 0.0
+    d = S.diagonal(dim1=1, dim2=2)
+    assert d.imag.abs().max().item() == 0.0 and d.real.min().item() > 0
+    # one full frequency against the oracle's definition from GPU spectra-free math
+    want = oc.trial_average([oc.cross_spectra_cF(t.copy(), 1000., taper="hann", polyremoval=0,
+                                                 foi=np.array([100.0]))[0] for t in trials])
+    k = int(np.argmin(np.abs(res.freqs - 100.0)))
+    got = (S[k] / 8).cpu().numpy()
+    assert nerr(got, want[0, 0]) <= 1e-5

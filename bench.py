@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the hot path on BASELINE.json's metric:
+
+    trial-spectra/s for mtmfft + ST_CrossSpectra coherence on 200 trials x 256 channels x
+    4096 samples float32 per GPU (BASELINE configs[1]; weak scaling over GPUs: every rank
+    owns 200 trials, the trial-summed CSD is all-reduced over NCCL, then normalised).
+
+One "step" = one full pass over the rank's 200 synthetic trials:
+    tapered FFT (K1) -> cross-spectral contraction over all trials (K2) -> [all-reduce] ->
+    coherency |C_ij| (K3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--taper hann|dpss] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric
+through the public API with pinned host buffers and H2D / D2H copies inside the timed region.
+`--impl reference` times the reference's own CPU algorithm (the NumPy oracle port, one process
+per host core, one task per trial like its Dask path) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_TRIALS, N_SAMPLES, N_CHAN, FS = 200, 4096, 256, 1000.0
+METRIC = "trial-spectra/s (mtmfft+CSD coherence, 256ch/4096smp)"
+UNIT = "trial-spectra/s"
+
+
+def workload_cfg(taper):
+    if taper == "dpss":
+        # tapsmofrq = 4*fs/4096 -> NW = 4, Kmax = 7
+        return dict(taper="dpss", taper_opt={"NW": 4.0, "Kmax": 7}, K=7)
+    return dict(taper="hann", taper_opt=None, K=1)
+
+
+def config_dict(args, n_gpus):
+    w = workload_cfg(args.taper)
+    return {
+        "workload": f"cfg-2: mtmfft+ST_CrossSpectra coherence, {N_TRIALS} trials x {N_CHAN} ch x "
+                    f"{N_SAMPLES} smp fp32 per GPU, taper={w['taper']} (K={w['K']}), polyremoval=0, "
+                    f"foi=None (2049 bins), output=abs, keeptrials=False",
+        "trials_per_gpu": N_TRIALS, "n_channels": N_CHAN, "n_samples": N_SAMPLES, "n_tapers": w["K"],
+        "parallelism": f"trial-sharded x{n_gpus}" + (" + NCCL all-reduce of the CSD sum" if n_gpus > 1 else ""),
+        "l2_policy": "inputs (839 MB/step) and spectra exceed the 126 MB L2; no explicit flush",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on host cores
+# ----------------------------------------------------------------------------------------------
+
+def _cpu_one_trial(job):
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    seed, taper, taper_opt = job
+    from oracle import connectivity as oc
+    from oracle import synth
+    x = synth.white_noise_trial(N_SAMPLES, N_CHAN, seed)
+    cs, _ = oc.cross_spectra_cF(x, FS, taper=taper, taper_opt=taper_opt, polyremoval=0)
+    return cs
+
+
+def cpu_reference_sample(taper, n_workers=None, trials_per_worker=1):
+    """One task per trial over a process pool (the reference's Dask LocalCluster semantics,
+    computational_routine.py:926-930), trial sum + mean + normalisation in the parent."""
+    from oracle import connectivity as oc
+    from oracle import synth
+    w = workload_cfg(taper)
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        mem_gb = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        mem_gb = 64
+    per_proc_gb = 4.5 + 1.1 * w["K"]          # [K, F, C, C] complex64 temporaries of the reference
+    if n_workers is None:
+        n_workers = int(max(1, min(cores, 32, mem_gb // per_proc_gb)))
+    n_trials = n_workers * trials_per_worker
+    seeds = synth.trial_seeds(n_trials)
+    jobs = [(int(s), w["taper"], w["taper_opt"]) for s in seeds]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(n_workers) as pool:
+        acc = None
+        for cs in pool.imap_unordered(_cpu_one_trial, jobs):
+            acc = cs.copy() if acc is None else acc.__iadd__(cs)
+    acc /= n_trials
+    coh = oc.normalize_csd(acc, "abs")
+    dt = time.perf_counter() - t0
+    assert np.isfinite(coh).all()
+    return dict(value=n_trials / dt, unit=UNIT, cores=n_workers, kind="port",
+                sample=f"{n_trials} trials of the workload ({trials_per_worker}/worker, one process per worker, "
+                       f"1 BLAS thread each; incl. trial mean + normalize_csd), {dt:.1f} s wall"), dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals, times = [], []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info, dt = cpu_reference_sample(args.taper)
+        if i >= args.warmup:
+            vals.append(info["value"])
+            times.append(dt)
+    value = float(np.mean(vals))
+    info["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT in f64, CSD in c64)",
+        "data": "synthetic", "config": config_dict(args, args.gpus), "cpu_baseline": info,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                p = [s.strip() for s in ln.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); smax.append(float(p[2])); power.append(float(p[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # "under load": samples at or above the median power draw
+            med_p = float(np.median(power))
+            load = [s for s, pw in zip(sm, power) if pw >= med_p] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        pk = json.load(open(path))
+        return dict(hbm_gbs=pk["hbm_gbs"], bf16_tflops=pk["bf16_tflops"],
+                    bf16_tflops_sustained=pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import synth                       # input generator only (checker-side code)
+    from syncopy_b200 import _lib, batched
+    from syncopy_b200 import hostmath as hm
+    from syncopy_b200.engine import get_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    eng = get_engine(local_rank)
+    dev = eng.tdev
+    w = workload_cfg(args.taper)
+    K = w["K"]
+
+    # ---- synthetic trials: white noise, per-trial seeds as syncopy.synthdata (seed 42), shard = rank
+    seeds = synth.trial_seeds(N_TRIALS * world)[rank * N_TRIALS:(rank + 1) * N_TRIALS]
+    host = torch.empty((N_TRIALS, N_SAMPLES, N_CHAN), dtype=torch.float32).pin_memory()
+    hnp = host.numpy()
+    for k, s in enumerate(seeds):
+        hnp[k] = synth.white_noise_trial(N_SAMPLES, N_CHAN, int(s))
+    x = host.to(dev)
+
+    n_freq = N_SAMPLES // 2 + 1
+    tapers = eng.taper_table(w["taper"], N_SAMPLES, N_SAMPLES, w["taper_opt"])
+    scale = hm.mtmfft_scale(N_SAMPLES, N_SAMPLES)
+    spectra = torch.empty((n_freq, N_TRIALS * K, N_CHAN), dtype=torch.complex64, device=dev)
+    csd_sum = torch.empty((n_freq, N_CHAN, N_CHAN), dtype=torch.complex64, device=dev)
+    coh = torch.empty((1, n_freq, N_CHAN, N_CHAN), dtype=torch.float32, device=dev)
+    coh_host = torch.empty(coh.shape, dtype=torch.float32).pin_memory()
+    total_trials = N_TRIALS * world
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+
+    def step(marks=None):
+        if marks is not None:
+            marks[0].record()
+        eng.mtmfft(x, tapers, N_SAMPLES, scale, polyremoval=0, output="fourier", keeptapers=True,
+                   out=spectra, freq_major=True)
+        if marks is not None:
+            marks[1].record()
+        eng.csd_accumulate(spectra, acc=csd_sum, alpha=1.0 / K, beta=0.0, impl=args.csd_impl)
+        if marks is not None:
+            marks[2].record()
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(csd_sum))
+        if marks is not None:
+            marks[3].record()
+        eng.csd_normalize(csd_sum[None], output="abs", pre_scale=1.0 / total_trials, out=coh)
+        if marks is not None:
+            marks[4].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    marks = [[ev() for _ in range(5)] for _ in range(args.steps)]
+    launches0 = _lib.launch_count()
+    barrier()
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    for i in range(args.steps):
+        step(marks[i])
+    t_end.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    seg = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(4)] for m in marks])   # ms: fft, csd, allreduce, norm
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = total_trials * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API (pinned host in, pinned host out) ---------------------
+    def e2e_step():
+        c, _ = batched.coherence(host, FS, taper=w["taper"], taper_opt=w["taper_opt"], polyremoval=0,
+                                 output="abs", engine=eng, impl=args.csd_impl,
+                                 reduce_group=(dist.group.WORLD if world > 1 else None), out_host=coh_host)
+        return c
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = ev(), ev()
+    e2e_steps = max(2, min(args.steps, 5))
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tmax.item())
+    e2e_value = total_trials * e2e_steps / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # quick self-check of the e2e result against the device-resident one
+    assert torch.isfinite(coh).all()
+    dmax = (coh_host.to(dev) - coh).abs().max().item()
+    assert dmax < 1e-5, f"e2e result deviates from device-resident result ({dmax})"
+
+    if rank == 0:
+        peaks = load_peaks()
+        fft_ms, csd_ms, ar_ms, norm_ms = seg.mean(axis=0)
+        in_bytes = N_TRIALS * N_SAMPLES * N_CHAN * 4
+        spec_bytes = n_freq * N_TRIALS * K * N_CHAN * 8
+        csd_bytes = n_freq * N_CHAN * N_CHAN * 8
+        flops_alg = 8.0 * N_CHAN * N_CHAN * n_freq * K * N_TRIALS          # 1.074 GFLOP * K per trial
+        alg_bytes_per_trial = 4 * N_SAMPLES * N_CHAN + csd_bytes / N_TRIALS   # 9,565,635 B (T = 200)
+        tensor_peak = peaks["bf16_tflops_sustained"]
+        achieved_tf = flops_alg / (csd_ms * 1e-3) / 1e12
+        roofline = {
+            "kernel": "csd contraction (K2)", "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak,
+            "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak, "traffic": None,
+            "peak_source": f"{peaks['source']} bf16 dense sustained (kernel timed inside a long step)",
+            "algorithmic": f"8*C^2*nFreq*K flop per trial = {flops_alg / N_TRIALS / 1e9:.3f} GFLOP, x{N_TRIALS} trials/launch",
+            "share_of_step": float(csd_ms / ms_per_step),
+        }
+        kernels = {
+            "mtmfft (K1)": {"ms": float(fft_ms), "bound": "hbm",
+                            "achieved_gbs": (in_bytes + spec_bytes) / (fft_ms * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": (in_bytes + spec_bytes) / (fft_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "csd (K2)": {"ms": float(csd_ms), "bound": "tensor", "achieved_tflops": achieved_tf,
+                         "bytes_gbs": (spec_bytes + csd_bytes) / (csd_ms * 1e-3) / 1e9},
+            "allreduce": {"ms": float(ar_ms)},
+            "normalize (K3)": {"ms": float(norm_ms), "bound": "hbm",
+                               "achieved_gbs": (csd_bytes * 1.5) / (norm_ms * 1e-3) / 1e9},
+        }
+        hbm_pipeline = {
+            "algorithmic_bytes_per_trial": alg_bytes_per_trial,
+            "achieved_gbs": alg_bytes_per_trial * value / world / 1e9,
+            "frac_of_hbm_peak": alg_bytes_per_trial * value / world / 1e9 / peaks["hbm_gbs"],
+        }
+        cpu_info = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_info, _ = cpu_reference_sample(args.taper)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": coh.numel() * 4, "steps": e2e_steps,
+                    "api": "syncopy_b200.batched.coherence(pinned host trials) -> pinned host coherence"},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": kernels, "hbm_pipeline": hbm_pipeline,
+            "cpu_baseline": cpu_info, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--taper", default="hann", choices=["hann", "dpss"])
+    ap.add_argument("--csd-impl", dest="csd_impl", type=int, default=0, help="0 auto, 1 SIMT, 2 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

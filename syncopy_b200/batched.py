@@ -22,7 +22,7 @@ MAX_SPECTRA_BYTES = 24 << 30
 def _device_trials(eng, trials):
     if isinstance(trials, torch.Tensor):
         assert trials.dim() == 3
-        return trials.to(device=eng.tdev, dtype=torch.float32).contiguous()
+        return trials.to(device=eng.tdev, dtype=torch.float32, non_blocking=True).contiguous()
     arr = np.ascontiguousarray(trials, dtype=np.float32)
     assert arr.ndim == 3, "trials must be [nTrials, nSamples, nChannels]"
     return torch.from_numpy(arr).to(eng.tdev, non_blocking=True)
@@ -170,18 +170,36 @@ def cross_spectra(trials, samplerate=1, nSamples=None, foi=None, taper="hann", t
     return csd, freqs
 
 
+def _finish(result, to_host, out_host):
+    """Optionally move a CUDA result to the host (into a caller-provided pinned tensor if given)."""
+    if out_host is not None:
+        out_host.copy_(result, non_blocking=True)
+        torch.cuda.current_stream(result.device).synchronize()
+        return out_host
+    if to_host:
+        return result.cpu().numpy()
+    return result
+
+
 def coherence(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_opt=None,
-              polyremoval=0, output="abs", to_host=False, engine=None, impl=0):
+              polyremoval=0, output="abs", to_host=False, engine=None, impl=0, reduce_group=None,
+              out_host=None):
     """
     `connectivityanalysis(method='coh')` compute chain: CrossSpectra(keeptrials=False) followed by
     NormalizeCrossSpectra (syncopy/connectivity/connectivity_analysis.py:460-473,549,587-599,677-679).
     The 1/nTrials of the trial mean is folded into the normalisation kernel.
-    Returns (coh [1, nFreq, C, C], freqs).
+
+    With `reduce_group` (a torch.distributed process group) `trials` is this rank's shard of the
+    trial list: the trial-summed CSD and the trial count are all-reduced (the one collective of the
+    path, replacing the reference's lock-serialised HDF5 `+=`, kwarg_decorators.py:722-735) and every
+    rank returns the full result.  Returns (coh [1, nFreq, C, C], freqs).
     """
     eng = engine or get_engine()
     res = cross_spectra_sum(trials, samplerate, nSamples, foi, taper, taper_opt, False, polyremoval,
                             engine=eng, impl=impl)
-    coh = eng.csd_normalize(res.csd_sum[None], output=output, pre_scale=1.0 / res.n_trials)
-    if to_host:
-        coh = coh.cpu().numpy()
-    return coh, res.freqs
+    n_total = res.n_trials
+    if reduce_group is not None:
+        from .distributed import allreduce_csd
+        n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group)
+    coh = eng.csd_normalize(res.csd_sum[None], output=output, pre_scale=1.0 / n_total)
+    return _finish(coh, to_host, out_host), res.freqs

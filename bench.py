@@ -228,7 +228,11 @@ def run_gpu_arm(args):
     n_freq = N_SAMPLES // 2 + 1
     tapers = eng.taper_table(w["taper"], N_SAMPLES, N_SAMPLES, w["taper_opt"])
     scale = hm.mtmfft_scale(N_SAMPLES, N_SAMPLES)
-    spectra = torch.empty((n_freq, N_TRIALS * K, N_CHAN), dtype=torch.complex64, device=dev)
+    use_tc = args.csd_impl == 2 or (args.csd_impl == 0 and eng.csd_planar_supported(N_CHAN))
+    if use_tc:      # planar re|im rows: operand layout of the tcgen05 cross-spectral kernel
+        spectra = torch.empty((n_freq, N_TRIALS * K, 2, N_CHAN), dtype=torch.float32, device=dev)
+    else:
+        spectra = torch.empty((n_freq, N_TRIALS * K, N_CHAN), dtype=torch.complex64, device=dev)
     csd_sum = torch.empty((n_freq, N_CHAN, N_CHAN), dtype=torch.complex64, device=dev)
     coh = torch.empty((1, n_freq, N_CHAN, N_CHAN), dtype=torch.float32, device=dev)
     coh_host = torch.empty(coh.shape, dtype=torch.float32).pin_memory()
@@ -239,11 +243,14 @@ def run_gpu_arm(args):
     def step(marks=None):
         if marks is not None:
             marks[0].record()
-        eng.mtmfft(x, tapers, N_SAMPLES, scale, polyremoval=0, output="fourier", keeptapers=True,
-                   out=spectra, freq_major=True)
+        eng.mtmfft(x, tapers, N_SAMPLES, scale, polyremoval=0, output="fourier_planar" if use_tc else "fourier",
+                   keeptapers=True, out=spectra, freq_major=True)
         if marks is not None:
             marks[1].record()
-        eng.csd_accumulate(spectra, acc=csd_sum, alpha=1.0 / K, beta=0.0, impl=args.csd_impl)
+        if use_tc:
+            eng.csd_accumulate_planar(spectra, acc=csd_sum, alpha=1.0 / K, beta=0.0)
+        else:
+            eng.csd_accumulate(spectra, acc=csd_sum, alpha=1.0 / K, beta=0.0, impl=1)
         if marks is not None:
             marks[2].record()
         if world > 1:
@@ -326,7 +333,7 @@ def run_gpu_arm(args):
         tensor_peak = peaks["bf16_tflops_sustained"]
         achieved_tf = flops_alg / (csd_ms * 1e-3) / 1e12
         roofline = {
-            "kernel": "csd contraction (K2)", "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak,
+            "kernel": "csd contraction (K2, %s)" % ("tcgen05 3xTF32" if use_tc else "CUDA-core FP32"), "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak,
             "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak, "traffic": None,
             "peak_source": f"{peaks['source']} bf16 dense sustained (kernel timed inside a long step)",
             "algorithmic": f"8*C^2*nFreq*K flop per trial = {flops_alg / N_TRIALS / 1e9:.3f} GFLOP, x{N_TRIALS} trials/launch",

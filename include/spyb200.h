@@ -9,7 +9,10 @@
  *   - trials are C-contiguous [trial][sample][channel] float32 (AnalogData default dimord,
  *     reference syncopy/datatype/continuous_data.py:405); complex64 is interleaved (re, im);
  *   - `out_kind` follows syncopy/shared/const_def.py:25-40:
- *       0 pow, 1 abs, 2 fourier/complex, 3 real, 4 imag, 5 angle, 6 absreal, 7 absimag.
+ *       0 pow, 1 abs, 2 fourier/complex, 3 real, 4 imag, 5 angle, 6 absreal, 7 absimag;
+ *     spyb_mtmfft additionally accepts 8 = complex result as two float32 planes (re at the element
+ *     offset, im n_chan floats later; output strides then count floats) -- the operand layout of
+ *     spyb_csd_accumulate_planar.
  *
  * The reference has no FFI (it is pure Python); the interface each entry point replaces is
  * the NumPy-level function cited next to it.  INTEGRATION.md shows the ctypes binding and the
@@ -87,6 +90,20 @@ int spyb_mtmconvol(const float* x, int n_trials, long long trial_stride, int n_s
 int spyb_csd_accumulate(const void* spectra, long long sx_f, long long sx_r, int n_rows, int n_freq, int n_chan,
                         const int* idx_i, int n_i, const int* idx_j, int n_j,
                         float alpha, float beta, void* acc, int impl, void* stream);
+
+/*
+ * The same contraction on the tcgen05 tensor cores (3xTF32 split, FP32 accumulation in TMEM), for the
+ * whole-dataset path where all (trial, taper) rows of a frequency are reduced in one launch
+ * (csd.py:98-102 + computational_routine.py:1022-1025).
+ *   planes   float32 "planar" spectra as written by spyb_mtmfft with out_kind = 8:
+ *            element (f, r, plane, c) at f*sx_f + r*sx_r + plane*n_chan + c, plane 0 = real, 1 = imaginary
+ *   acc      complex64 [n_freq][n_chan][n_chan], acc = beta*acc + alpha * sum_r X_r X_r^H
+ * spyb_csd_planar_supported() tells whether a shape is eligible (n_chan in {128, 256}, strides % 4 == 0);
+ * ineligible shapes go through spyb_csd_accumulate.
+ */
+int spyb_csd_planar_supported(int n_chan, long long sx_f, long long sx_r);
+int spyb_csd_accumulate_planar(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                               int n_chan, float alpha, float beta, void* acc, void* stream);
 
 /*
  * Coherency + output conversion:  out = conv( pre*C_ij / sqrt(pre*C_ii * pre*C_jj) ).

@@ -32,6 +32,8 @@ PROTOTYPES = {
     "spyb_mtmconvol": (_i, [_vp, _i, _ll, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _i, _i, _i,
                             _vp, _ll, _ll, _ll, _ll, _vp]),
     "spyb_csd_accumulate": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _vp, _i, _f, _f, _vp, _i, _vp]),
+    "spyb_csd_planar_supported": (_i, [_i, _ll, _ll]),
+    "spyb_csd_accumulate_planar": (_i, [_vp, _ll, _ll, _i, _i, _i, _f, _f, _vp, _vp]),
     "spyb_csd_normalize": (_i, [_vp, _ll, _i, _f, _i, _vp, _vp]),
     "spyb_scale": (_i, [_vp, _ll, _f, _vp]),
 }

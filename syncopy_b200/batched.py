@@ -126,17 +126,27 @@ def cross_spectra_sum(trials, samplerate=1, nSamples=None, foi=None, taper="hann
     scale = hm.mtmfft_scale(n_sig, nfft)
     pr = hm.polyremoval_code(polyremoval)
 
+    # impl: 0 auto (tcgen05 kernel when the shape is eligible), 1 CUDA-core FP32 kernel, 2 tcgen05 kernel
+    use_tc = impl == 2 or (impl == 0 and eng.csd_planar_supported(n_chan))
     bytes_per_trial = n_freq * K * n_chan * 8
     chunk = max(1, min(B, MAX_SPECTRA_BYTES // max(1, bytes_per_trial)))
     acc = out
-    spectra = torch.empty((n_freq, min(chunk, B) * K, n_chan), dtype=torch.complex64, device=eng.tdev)
+    rows = min(chunk, B) * K
+    if use_tc:
+        spectra = torch.empty((n_freq, rows, 2, n_chan), dtype=torch.float32, device=eng.tdev)
+    else:
+        spectra = torch.empty((n_freq, rows, n_chan), dtype=torch.complex64, device=eng.tdev)
     for b0 in range(0, B, chunk):
         nb = min(chunk, B - b0)
-        view = spectra[:, :nb * K, :]
+        view = spectra[:, :nb * K]
+        beta = 0.0 if (b0 == 0 and out is None) else 1.0
         eng.mtmfft(x[b0:b0 + nb], tapers, nfft, scale, polyremoval=pr, demean_taper=demean_taper,
-                   freq_idx=fidx, output="fourier", keeptapers=True, out=view, freq_major=True)
-        acc = eng.csd_accumulate(view, acc=acc, alpha=1.0 / K, beta=0.0 if (b0 == 0 and out is None) else 1.0,
-                                 impl=impl)
+                   freq_idx=fidx, output="fourier_planar" if use_tc else "fourier", keeptapers=True,
+                   out=view, freq_major=True)
+        if use_tc:
+            acc = eng.csd_accumulate_planar(view, acc=acc, alpha=1.0 / K, beta=beta)
+        else:
+            acc = eng.csd_accumulate(view, acc=acc, alpha=1.0 / K, beta=beta, impl=1)
     return CrossSpectraSum(acc, B, freqs)
 
 

@@ -45,7 +45,7 @@ int spyb_mtmfft(const float* x, int n_trials, long long trial_stride, int n_samp
                 void* out, long long so_trial, long long so_taper, long long so_freq,
                 float* chan_amax, void* stream) {
     if (nfft < n_samples) return fail("nfft (%d) must be >= n_samples (%d)", nfft, n_samples);
-    if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
+    if (out_kind < 0 || out_kind > 8) return fail("bad out_kind %d", out_kind);
     MtmFramesDesc d;
     d.x = x; d.trial_stride = trial_stride;
     d.n_trials = n_trials; d.n_samples = n_samples; d.n_chan = n_chan;
@@ -91,8 +91,21 @@ int spyb_csd_accumulate(const void* spectra, long long sx_f, long long sx_r, int
     d.n_rows = n_rows; d.n_freq = n_freq; d.n_chan = n_chan;
     d.idx_i = idx_i; d.idx_j = idx_j; d.n_i = n_i; d.n_j = n_j;
     d.alpha = alpha; d.beta = beta; d.acc = acc;
-    if (impl == 2) return fail("tensor-core CSD kernel not available in this build");
+    if (impl == 2) return fail("the tcgen05 kernel takes planar spectra: call spyb_csd_accumulate_planar");
     return csd_accumulate_simt(d, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_csd_planar_supported(int n_chan, long long sx_f, long long sx_r) {
+    return csd_tc_supported(n_chan, sx_f, sx_r) ? 1 : 0;
+}
+
+int spyb_csd_accumulate_planar(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                               int n_chan, float alpha, float beta, void* acc, void* stream) {
+    CsdPlanarDesc d;
+    d.planes = planes; d.sx_f = sx_f; d.sx_r = sx_r;
+    d.n_rows = n_rows; d.n_freq = n_freq; d.n_chan = n_chan;
+    d.alpha = alpha; d.beta = beta; d.acc = acc;
+    return csd_accumulate_tc(d, static_cast<cudaStream_t>(stream));
 }
 
 int spyb_csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind,

@@ -58,7 +58,10 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
 // output conversions of syncopy/shared/const_def.py:25-40 (spectralConversions)
 enum OutKind : int {
     OUT_POW = 0, OUT_ABS = 1, OUT_FOURIER = 2, OUT_REAL = 3, OUT_IMAG = 4,
-    OUT_ANGLE = 5, OUT_ABSREAL = 6, OUT_ABSIMAG = 7
+    OUT_ANGLE = 5, OUT_ABSREAL = 6, OUT_ABSIMAG = 7,
+    // engine-internal: complex result as two float32 planes, re at the element offset and im `n_chan`
+    // floats later ([..][re|im][channel]); the operand layout of the tcgen05 cross-spectral kernel
+    OUT_FOURIER_PLANAR = 8
 };
 __host__ __device__ __forceinline__ bool out_is_complex(int kind) { return kind == OUT_FOURIER; }
 

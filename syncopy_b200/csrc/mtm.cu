@@ -223,7 +223,17 @@ __global__ void __launch_bounds__(MAXT, MINB) mtm_kernel(const MtmArgs a) {
                                   (long long)fi * a.so_freq + c;
             const bool first = a.keeptapers || k == 0;
             const bool lastk = !a.keeptapers && k == a.n_tapers - 1 && a.n_tapers > 1;
-            if (a.out_kind == OUT_FOURIER) {
+            if (a.out_kind == OUT_FOURIER_PLANAR) {
+                // strides are in floats; re plane at `off`, im plane n_chan floats later (keeptapers only)
+                float* o = reinterpret_cast<float*>(a.out) + off;
+                if (a.vec_out && cb_ok) {
+                    *reinterpret_cast<float2*>(o) = make_float2(xa.x, xb.x);
+                    *reinterpret_cast<float2*>(o + a.n_chan) = make_float2(xa.y, xb.y);
+                } else {
+                    o[0] = xa.x; o[a.n_chan] = xa.y;
+                    if (cb_ok) { o[1] = xb.x; o[a.n_chan + 1] = xb.y; }
+                }
+            } else if (a.out_kind == OUT_FOURIER) {
                 float2* o = reinterpret_cast<float2*>(a.out) + off;
                 float2 ra = xa, rb = xb;
                 if (a.vec_out && cb_ok) {
@@ -352,6 +362,8 @@ int mtm_frames(const MtmFramesDesc& d, cudaStream_t stream) {
     const bool even_in = (d.n_chan % 2 == 0) && (d.trial_stride % 2 == 0) &&
                          (reinterpret_cast<uintptr_t>(d.x) % 8 == 0);
     a.vec_in = even_in ? 1 : 0;
+    if (d.out_kind == OUT_FOURIER_PLANAR && !d.keeptapers)
+        return fail("planar complex output needs keeptapers = 1");
     const size_t elem = out_is_complex(d.out_kind) ? 8 : 4;
     const bool even_out = (d.so_trial % 2 == 0) && (d.so_frame % 2 == 0) && (d.so_taper % 2 == 0) &&
                           (d.so_freq % 2 == 0) && (reinterpret_cast<uintptr_t>(d.out) % (2 * elem) == 0);

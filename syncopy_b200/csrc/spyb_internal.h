@@ -39,6 +39,17 @@ struct CsdDesc {
     void* acc = nullptr;             // device complex64 [n_freq][Ci][Cj]
 };
 int csd_accumulate_simt(const CsdDesc& d, cudaStream_t stream);
+
+// Same contraction from planar spectra float32 [f][r][re|im][c] on tcgen05 tensor cores (csd_tc.cu)
+struct CsdPlanarDesc {
+    const float* planes = nullptr;   // device, element (f, r, plane, c) at f*sx_f + r*sx_r + plane*n_chan + c
+    long long sx_f = 0, sx_r = 0;    // in floats
+    int n_rows = 0, n_freq = 0, n_chan = 0;
+    float alpha = 1.f, beta = 0.f;
+    void* acc = nullptr;             // device complex64 [n_freq][C][C]
+};
+bool csd_tc_supported(int n_chan, long long sx_f, long long sx_r);
+int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream);
 int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind, void* out,
                   cudaStream_t stream);
 int scale_inplace(float* x, long long n, float s, cudaStream_t stream);

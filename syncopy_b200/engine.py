@@ -80,16 +80,25 @@ class Engine:
         B, N, Cn = x.shape
         K = tapers.shape[0]
         assert tapers.shape[1] == N and tapers.is_contiguous()
-        kind = hm.out_kind(output)
+        planar = output == "fourier_planar"
+        kind = 8 if planar else hm.out_kind(output)
         fidx = self.index_table(freq_idx)
         nF = (nfft // 2 + 1) if fidx is None else fidx.numel()
         Kout = K if keeptapers else 1
         dt = _CDTYPE[kind == 2]
-        shape = (nF, B * Kout, Cn) if freq_major else (B, Kout, nF, Cn)
+        if planar:
+            # float32 [nF, R, 2, C]: the operand layout of the tcgen05 cross-spectral kernel
+            assert freq_major and keeptapers
+            shape = (nF, B * Kout, 2, Cn)
+        else:
+            shape = (nF, B * Kout, Cn) if freq_major else (B, Kout, nF, Cn)
         if out is None:
             out = torch.empty(shape, dtype=dt, device=self.tdev)
         assert out.is_cuda and out.dtype == dt and tuple(out.shape) == shape
-        if freq_major:
+        if planar:
+            assert out[0].is_contiguous()
+            so_freq, so_trial, so_taper = (out.stride(0) if nF > 1 else 0), Kout * 2 * Cn, 2 * Cn
+        elif freq_major:
             # `out` may be a row-slice of a larger [nF, R, C] buffer (trial chunks)
             assert out[0].is_contiguous()
             so_freq, so_trial, so_taper = (out.stride(0) if nF > 1 else 0), Kout * Cn, Cn
@@ -149,6 +158,26 @@ class Engine:
         _lib.check(self.lib.spyb_csd_accumulate(
             spectra.data_ptr(), (spectra.stride(0) if nF > 1 else 0), Cn, R, nF, Cn,
             _ptr(ti), Ci, _ptr(tj), Cj, float(alpha), float(beta), acc.data_ptr(), int(impl), self.stream()))
+        return acc
+
+    def csd_planar_supported(self, n_chan):
+        return bool(self.lib.spyb_csd_planar_supported(int(n_chan), 4, 4))
+
+    def csd_accumulate_planar(self, planes, acc=None, alpha=1.0, beta=0.0):
+        """
+        planes [nF, R, 2, C] float32 (re / im planes per row, from `mtmfft(output="fourier_planar")`),
+        acc [nF, C, C] complex64: acc = beta*acc + alpha * sum_r X_r X_r^H on the tcgen05 tensor cores.
+        """
+        assert planes.is_cuda and planes.dtype == torch.float32 and planes.dim() == 4 and planes.shape[2] == 2
+        nF, R, _, Cn = planes.shape
+        assert planes[0].is_contiguous()
+        if acc is None:
+            acc = torch.empty((nF, Cn, Cn), dtype=torch.complex64, device=self.tdev)
+            beta = 0.0
+        assert acc.is_contiguous() and acc.shape == (nF, Cn, Cn) and acc.dtype == torch.complex64
+        _lib.check(self.lib.spyb_csd_accumulate_planar(
+            planes.data_ptr(), (planes.stride(0) if nF > 1 else 2 * R * Cn), 2 * Cn, R, nF, Cn,
+            float(alpha), float(beta), acc.data_ptr(), self.stream()))
         return acc
 
     def csd_normalize(self, csd, output="abs", pre_scale=1.0, out=None):

@@ -128,3 +128,36 @@ def test_cfg2_shape_properties(engine):
     k = int(np.argmin(np.abs(res.freqs - 100.0)))
     got = (S[k] / 8).cpu().numpy()
     assert nerr(got, want[0, 0]) <= 1e-5
+
+
+@pytest.mark.parametrize("n_trials,n,c,taper,opt", [(5, 256, 256, "hann", None),
+                                                    (3, 128, 128, "dpss", {"NW": 2, "Kmax": 3}),
+                                                    (11, 64, 256, "hann", None)])
+def test_tcgen05_csd_vs_oracle(engine, n_trials, n, c, taper, opt):
+    """Tensor-core contraction (3xTF32, TMEM accumulators) against the oracle's complex64 outer product."""
+    import torch
+    from syncopy_b200 import batched
+    assert engine.csd_planar_supported(c)
+    trials = synth.white_noise(n_trials, n, c)
+    trials[:, :, 1] *= 300.0                      # wide dynamic range across channels
+    trials[:, :, 2] = trials[:, :, 1] * 1e-3 + trials[:, :, 2]
+    res = batched.cross_spectra_sum(trials, 1000., taper=taper, taper_opt=opt, polyremoval=0, impl=2)
+    simt = batched.cross_spectra_sum(trials, 1000., taper=taper, taper_opt=opt, polyremoval=0, impl=1)
+    S = res.csd_sum
+    assert (S - S.conj().transpose(1, 2)).abs().max().item() == 0.0
+    assert S.diagonal(dim1=1, dim2=2).imag.abs().max().item() == 0.0
+    want = oc.trial_average([oc.cross_spectra_cF(t.copy(), 1000., taper=taper, taper_opt=opt, polyremoval=0)[0]
+                             for t in trials])
+    got = res.average().cpu().numpy()
+    # per-frequency normwise error, and error relative to sqrt(S_ii S_jj) (what coherence sees)
+    w = want[0].astype(np.complex128)
+    err = np.abs(got[0] - w)
+    assert (err.max(axis=(1, 2)) / np.abs(w).max(axis=(1, 2))).max() <= TOL
+    d = np.sqrt(np.abs(np.einsum("fii->fi", w)))
+    assert (err / (d[:, :, None] * d[:, None, :])).max() <= TOL
+    assert nerr(S.cpu().numpy(), simt.csd_sum.cpu().numpy()) <= 2e-6
+    # accumulate-into (beta = 1) path used for trial chunks
+    twice = batched.cross_spectra_sum(trials, 1000., taper=taper, taper_opt=opt, polyremoval=0, impl=2,
+                                      out=S.clone())
+    assert nerr(twice.csd_sum.cpu().numpy(), 2 * S.cpu().numpy()) <= 1e-6
+    assert torch.isfinite(twice.csd_sum.abs()).all()

@@ -14,13 +14,16 @@
 // hi*hi + hi*lo + lo*hi, FP32 accumulation in TMEM), which keeps the result within ~5e-7 of an
 // FP32 product -- plain TF32 (10-bit mantissa) would miss the 1e-5 parity bar.
 //
-// One persistent CTA per SM; a work item is (frequency, 128-row block of the output):
-//   warp 0      TMA producer: one 5-D tiled bulk-tensor load per stage brings KC rows of both planes
-//               into shared memory, directly in the swizzled canonical MN-major layout (128B span, 32B atoms)
-//   warps 2..5  converter: split the landed FP32 tile into hi (in place) and lo planes
-//   warp 1      MMA issuer: 12 tcgen05.mma (M=128, N=C, K=8) per 8 rows, commits free the stage
-//   warps 6..9  epilogue: tcgen05.ld -> alpha/beta -> global store, once per accumulation chain
-// Accumulators: C_re in TMEM columns [0, C), C_im in [C, 2C); lane = output row.
+// One persistent CTA per SM (16 warps); a work item is (frequency, upper-triangular 128x128 output tile):
+//   warp 0       TMA producer: 5-D tiled bulk-tensor loads bring KC rows x 128 channels of the re and im
+//                planes of the tile's row block (and column block, if different) into shared memory,
+//                directly in the swizzled canonical MN-major layout (128B span, 32B atoms)
+//   warps 4..7   converter: split the landed FP32 tile into hi (in place) and lo planes
+//   warp 1       MMA issuer: 12 tcgen05.mma (M=128, N=128, K=8) per 8 rows into TMEM buffer b; a commit
+//                frees the stage, another one hands the buffer to the epilogue at the end of a chain
+//   warps 8..15  epilogue (208 registers each via setmaxnreg): pull every finished accumulation chain out
+//                of TMEM (tcgen05.ld) and sum the chains in registers; store the tile and its mirror
+// Accumulators: two TMEM buffers of 256 columns (C_re | C_im), lane = output row of the tile.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -33,17 +36,20 @@ namespace spyb {
 namespace {
 
 constexpr int TC_KC = 16;              // rows per pipeline stage (two K=8 MMA steps)
-constexpr int TC_THREADS = 320;        // 10 warps
-constexpr int TC_CONV_THREADS = 128;   // warps 2..5
-constexpr int TC_EPI_THREADS = 128;    // warps 6..9
+constexpr int TC_THREADS = 512;        // 16 warps = 4 warpgroups
+constexpr int TC_CONV_THREADS = 128;   // warps 4..7
+constexpr int TC_EPI_THREADS = 256;    // warps 8..15
+constexpr int TC_PLANE = TC_KC * 512;  // bytes: one plane (128 channels x KC rows) of a half-tile
+constexpr int TC_SLOT = 4 * TC_PLANE;  // half-tile: re_hi | im_hi | re_lo | im_lo
+constexpr int TC_STAGE = 2 * TC_SLOT;  // row-block half-tile (A) + column-block half-tile (B)
+constexpr int TC_STAGES = 3;
 
 struct TcArgs {
     int n_rows, n_freq, n_chan;
-    int n_mblk;                // 128-row blocks of the output
-    int cb_stride;             // 32-channel blocks per plane (= n_chan / 32)
-    int n_stages;
-    int tmem_cols;             // power of two >= 2*n_chan
-    int chain_ksteps;          // pipeline stages (of TC_KC rows) accumulated in TMEM before a flush
+    int n_tiles;               // upper-triangular 128x128 tiles per frequency (1 or 3)
+    int chain_ksteps;          // pipeline stages (of TC_KC rows) accumulated in TMEM before the FP32 flush
+    int store_mode;            // 0: per-thread row stores (debug), 1: shared-memory transposed, coalesced
+    int rewrite_hi;            // 1: store rna_tf32(x) back as the hi operand; 0: let the MMA truncate x itself
     float alpha, beta;
     float2* acc;               // [n_freq][C][C]
 };
@@ -54,16 +60,30 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// Bounded wait: a pipeline bug must surface as a launch error (trap) within seconds, never as a hung GPU.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    const uint32_t addr = smem_u32(bar);
+    uint64_t t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if ((spin & 1023u) == 1023u) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ull) __trap();       // 8 s without progress
+        }
+    }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -127,6 +147,9 @@ __device__ __forceinline__ float rna_tf32(float x) {
     return __uint_as_float(r);
 }
 
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+
 // Shared-memory matrix descriptor, MN-major 32-bit operands.  The only swizzled layout tcgen05 accepts
 // for MN-major TF32 is SWIZZLE_128B_BASE32B (32-byte chunks XOR-ed with the row index, 4-row period):
 // canonical layout ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) in floats = 32 channels x 4 rows per 512 B
@@ -147,215 +170,263 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Work items: (frequency f, 128-row block mblk).  Only the upper block triangle is computed: block row
-// mblk covers columns [128*mblk, C), so with two block rows the first is twice as heavy as the second.
-// Round k of the persistent loop hands CTA b the unit u = b + k*grid; flipping the block row with the
-// round parity (grid is even) makes every CTA alternate heavy / light items, while the two items of
-// one frequency still run in the same round on neighbouring CTAs (their operand tile is shared in L2).
-__device__ __forceinline__ void decode_item(int u, int round, int n_mblk, int& f, int& mblk) {
-    f = u / n_mblk;
-    mblk = u % n_mblk;
-    if (n_mblk == 2) mblk ^= (round & 1);
+// Work item = (frequency f, upper-triangular 128x128 output tile (ti, tj)); items of one frequency are
+// neighbours in the persistent round-robin, so their operand tiles are shared through L2.
+__device__ __forceinline__ void decode_item(int item, int n_tiles, int& f, int& ti, int& tj) {
+    f = item / n_tiles;
+    const int t = item - f * n_tiles;
+    ti = t >> 1;            // 0 -> (0,0), 1 -> (0,1), 2 -> (1,1)
+    tj = (t + 1) >> 1;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages][hi planes | lo planes] then barriers
-    const uint32_t plane_bytes = (uint32_t)a.cb_stride * TC_KC * 128u;      // one plane of one stage
-    const uint32_t half_bytes = 2u * plane_bytes;                          // re + im
-    const uint32_t stage_bytes = 2u * half_bytes;                          // hi + lo
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)a.n_stages * stage_bytes);
-    uint64_t* full_raw = bars;
-    uint64_t* full_conv = bars + a.n_stages;
-    uint64_t* empty = bars + 2 * a.n_stages;
-    uint64_t* acc_full = bars + 3 * a.n_stages;
-    uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)TC_STAGES * TC_STAGE);
+    uint64_t* full_raw = bars;                      // [stage]  TMA landed
+    uint64_t* full_conv = bars + TC_STAGES;         // [stage]  hi / lo split done
+    uint64_t* empty = bars + 2 * TC_STAGES;         // [stage]  MMAs reading the stage retired
+    uint64_t* acc_full = bars + 3 * TC_STAGES;      // [2]      chain accumulated in TMEM buffer b
+    uint64_t* acc_empty = acc_full + 2;             // [2]      epilogue drained TMEM buffer b
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float2* staging = reinterpret_cast<float2*>(acc_empty + 4);   // [8 epilogue warps][32 x 16] transpose buffers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = a.n_chan;
-    const int n_items = a.n_freq * a.n_mblk;
+    const int n_items = a.n_freq * a.n_tiles;
     const int n_ksteps = (a.n_rows + TC_KC - 1) / TC_KC;
-    const int chain_ksteps = a.chain_ksteps;                               // stages per accumulation chain
-    const uint32_t box_bytes = 4u * TC_KC * 128u;                          // bytes one TMA box delivers (128 channels)
+    const int chain_ksteps = a.chain_ksteps;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.n_stages; ++s) {
+        for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&full_raw[s], 1);
             mbar_init(&full_conv[s], TC_CONV_THREADS);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, TC_EPI_THREADS);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], TC_EPI_THREADS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, 512u);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (elect_one()) {
+    if (warp < 4) {
+        reg_dec<40>();
+        if (warp == 0) {
+            // ===== TMA producer =====
+            if (elect_one()) {
+                int s = 0;
+                uint32_t phase = 0;
+                for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                    int f, ti, tj;
+                    decode_item(item, a.n_tiles, f, ti, tj);
+                    const int n_slots = ti == tj ? 1 : 2;
+                    for (int ks = 0; ks < n_ksteps; ++ks) {
+                        mbar_wait(&empty[s], phase ^ 1u);
+                        mbar_arrive_expect_tx(&full_raw[s], (uint32_t)(n_slots * 2 * TC_PLANE));
+                        uint8_t* dst = base + (size_t)s * TC_STAGE;
+                        tma_load_5d(&tmap, &full_raw[s], dst, 0, ks * TC_KC, 4 * ti, 0, f);
+                        tma_load_5d(&tmap, &full_raw[s], dst + TC_PLANE, 0, ks * TC_KC, 4 * ti, 1, f);
+                        if (n_slots == 2) {
+                            tma_load_5d(&tmap, &full_raw[s], dst + TC_SLOT, 0, ks * TC_KC, 4 * tj, 0, f);
+                            tma_load_5d(&tmap, &full_raw[s], dst + TC_SLOT + TC_PLANE, 0, ks * TC_KC, 4 * tj, 1, f);
+                        }
+                        if (++s == TC_STAGES) { s = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer =====
+            constexpr uint32_t lbo = TC_KC * 128u, sbo = 512u;
+            constexpr uint32_t idesc_pos = make_idesc(128, 128, false);
+            constexpr uint32_t idesc_neg = make_idesc(128, 128, true);
             int s = 0;
-            uint32_t phase = 0;
-            for (int item = blockIdx.x, round = 0; item < n_items; item += gridDim.x, ++round) {
-                int f, mblk;
-                decode_item(item, round, a.n_mblk, f, mblk);
-                // one box = 128 channels x KC rows of one plane; only channels >= 128*mblk are needed
-                const int n_half = a.n_mblk - mblk;
+            uint32_t phase = 0, chain = 0;               // chain counts accumulation chains over all items
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int f, ti, tj;
+                decode_item(item, a.n_tiles, f, ti, tj);
+                const uint32_t b_slot = ti == tj ? 0u : (uint32_t)TC_SLOT;
                 for (int ks = 0; ks < n_ksteps; ++ks) {
-                    mbar_wait(&empty[s], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full_raw[s], box_bytes * 2u * (uint32_t)n_half);
-                    uint8_t* dst = base + (size_t)s * stage_bytes;
-                    for (int h = mblk; h < a.n_mblk; ++h) {
-                        tma_load_5d(&tmap, &full_raw[s], dst + (size_t)h * box_bytes, 0, ks * TC_KC, 4 * h, 0, f);
-                        tma_load_5d(&tmap, &full_raw[s], dst + plane_bytes + (size_t)h * box_bytes, 0, ks * TC_KC, 4 * h, 1, f);
+                    const int kc = ks % chain_ksteps;                  // position inside the accumulation chain
+                    const uint32_t buf = chain & 1u;
+                    if (kc == 0) {                                     // epilogue must have drained this TMEM buffer
+                        mbar_wait(&acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
                     }
-                    if (++s == a.n_stages) { s = 0; phase ^= 1u; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        const uint32_t lbo = TC_KC * 128u, sbo = 512u;
-        int s = 0;
-        uint32_t phase = 0, acc_phase = 0;
-        for (int item = blockIdx.x, round = 0; item < n_items; item += gridDim.x, ++round) {
-            int f, mblk;
-            decode_item(item, round, a.n_mblk, f, mblk);
-            const int N = C - 128 * mblk;                          // columns [128*mblk, C)
-            const uint32_t idesc_pos = make_idesc(128, N, false);
-            const uint32_t idesc_neg = make_idesc(128, N, true);
-            const uint32_t d_re = tmem_base, d_im = tmem_base + (uint32_t)N;
-            for (int ks = 0; ks < n_ksteps; ++ks) {
-                const int kc = ks % chain_ksteps;                  // position inside the accumulation chain
-                if (kc == 0) {                                     // the epilogue must have drained the previous chain
-                    mbar_wait(acc_empty, acc_phase ^ 1u);
+                    mbar_wait(&full_conv[s], phase);
                     tc_fence_after();
-                }
-                mbar_wait(&full_conv[s], phase);
-                tc_fence_after();
-                const bool chain_end = (kc == chain_ksteps - 1) || (ks == n_ksteps - 1);
-                if (elect_one()) {
-                    const uint32_t st = smem_u32(base + (size_t)s * stage_bytes);
-                    const uint32_t a_off = (uint32_t)mblk * 4u * lbo;      // 128 channels = 4 atoms of 32
+                    const bool chain_end = (kc == chain_ksteps - 1) || (ks == n_ksteps - 1);
+                    if (elect_one()) {
+                        const uint32_t d_re = tmem_base + buf * 256u, d_im = d_re + 128u;
+                        const uint32_t st = smem_u32(base + (size_t)s * TC_STAGE);
 #pragma unroll
-                    for (int kk = 0; kk < TC_KC / 8; ++kk) {
-                        const uint32_t k_off = (uint32_t)kk * 1024u;
-                        // rows and columns of this item both start at channel 128*mblk: A and B share descriptors
-                        const uint32_t re_hi = st + k_off + a_off, im_hi = st + plane_bytes + k_off + a_off;
-                        const uint32_t re_lo = re_hi + half_bytes, im_lo = im_hi + half_bytes;
-                        const uint64_t Dre_hi = make_smem_desc(re_hi, lbo, sbo), Dre_lo = make_smem_desc(re_lo, lbo, sbo);
-                        const uint64_t Dim_hi = make_smem_desc(im_hi, lbo, sbo), Dim_lo = make_smem_desc(im_lo, lbo, sbo);
-                        const uint32_t first = (kc > 0 || kk > 0) ? 1u : 0u;
-                        // C_re = Re^T Re + Im^T Im   (A = first operand, B = second; both read the same tile)
-                        umma_tf32(d_re, Dre_lo, Dre_hi, idesc_pos, first);
-                        umma_tf32(d_re, Dre_hi, Dre_lo, idesc_pos, 1u);
-                        umma_tf32(d_re, Dim_lo, Dim_hi, idesc_pos, 1u);
-                        umma_tf32(d_re, Dim_hi, Dim_lo, idesc_pos, 1u);
-                        umma_tf32(d_re, Dre_hi, Dre_hi, idesc_pos, 1u);
-                        umma_tf32(d_re, Dim_hi, Dim_hi, idesc_pos, 1u);
-                        // C_im = Im^T Re - Re^T Im
-                        umma_tf32(d_im, Dim_lo, Dre_hi, idesc_pos, first);
-                        umma_tf32(d_im, Dim_hi, Dre_lo, idesc_pos, 1u);
-                        umma_tf32(d_im, Dre_lo, Dim_hi, idesc_neg, 1u);
-                        umma_tf32(d_im, Dre_hi, Dim_lo, idesc_neg, 1u);
-                        umma_tf32(d_im, Dim_hi, Dre_hi, idesc_pos, 1u);
-                        umma_tf32(d_im, Dre_hi, Dim_hi, idesc_neg, 1u);
+                        for (int kk = 0; kk < TC_KC / 8; ++kk) {
+                            const uint32_t ka = st + (uint32_t)kk * 1024u, kb = ka + b_slot;
+                            const uint64_t Are_hi = make_smem_desc(ka, lbo, sbo);
+                            const uint64_t Aim_hi = make_smem_desc(ka + TC_PLANE, lbo, sbo);
+                            const uint64_t Are_lo = make_smem_desc(ka + 2 * TC_PLANE, lbo, sbo);
+                            const uint64_t Aim_lo = make_smem_desc(ka + 3 * TC_PLANE, lbo, sbo);
+                            const uint64_t Bre_hi = make_smem_desc(kb, lbo, sbo);
+                            const uint64_t Bim_hi = make_smem_desc(kb + TC_PLANE, lbo, sbo);
+                            const uint64_t Bre_lo = make_smem_desc(kb + 2 * TC_PLANE, lbo, sbo);
+                            const uint64_t Bim_lo = make_smem_desc(kb + 3 * TC_PLANE, lbo, sbo);
+                            const uint32_t first = (kc > 0 || kk > 0) ? 1u : 0u;
+                            // C_re = Re^T Re + Im^T Im
+                            umma_tf32(d_re, Are_lo, Bre_hi, idesc_pos, first);
+                            umma_tf32(d_re, Are_hi, Bre_lo, idesc_pos, 1u);
+                            umma_tf32(d_re, Aim_lo, Bim_hi, idesc_pos, 1u);
+                            umma_tf32(d_re, Aim_hi, Bim_lo, idesc_pos, 1u);
+                            umma_tf32(d_re, Are_hi, Bre_hi, idesc_pos, 1u);
+                            umma_tf32(d_re, Aim_hi, Bim_hi, idesc_pos, 1u);
+                            // C_im = Im^T Re - Re^T Im
+                            umma_tf32(d_im, Aim_lo, Bre_hi, idesc_pos, first);
+                            umma_tf32(d_im, Aim_hi, Bre_lo, idesc_pos, 1u);
+                            umma_tf32(d_im, Are_lo, Bim_hi, idesc_neg, 1u);
+                            umma_tf32(d_im, Are_hi, Bim_lo, idesc_neg, 1u);
+                            umma_tf32(d_im, Aim_hi, Bre_hi, idesc_pos, 1u);
+                            umma_tf32(d_im, Are_hi, Bim_hi, idesc_neg, 1u);
+                        }
+                        umma_commit(&empty[s]);                      // stage free once these MMAs retire
+                        if (chain_end) umma_commit(&acc_full[buf]);
                     }
-                    umma_commit(&empty[s]);                      // stage free once these MMAs retire
-                    if (chain_end) umma_commit(acc_full);
+                    __syncwarp();
+                    if (chain_end) ++chain;
+                    if (++s == TC_STAGES) { s = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (chain_end) acc_phase ^= 1u;
-                if (++s == a.n_stages) { s = 0; phase ^= 1u; }
             }
         }
-    } else if (warp < 6) {
-        // ===== converter (warps 2..5): FP32 tile -> hi (in place) + lo =====
-        const int ct = threadIdx.x - 64;                        // 0..127
+    } else if (warp < 8) {
+        // ===== converter (warps 4..7): FP32 tile -> hi (in place) + lo =====
+        reg_dec<56>();
+        const int ct = threadIdx.x - 128;                       // 0..127
         int s = 0;
         uint32_t phase = 0;
-        for (int item = blockIdx.x, round = 0; item < n_items; item += gridDim.x, ++round) {
-            int f, mblk;
-            decode_item(item, round, a.n_mblk, f, mblk);
-            const uint32_t skip_chunks = (uint32_t)mblk * (box_bytes / 16u);          // channels below 128*mblk are not loaded
-            const uint32_t plane_item_chunks = (uint32_t)(a.n_mblk - mblk) * (box_bytes / 16u);
-            const uint32_t item_chunks = 2u * plane_item_chunks;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int f, ti, tj;
+            decode_item(item, a.n_tiles, f, ti, tj);
+            const int n_slots = ti == tj ? 1 : 2;
             for (int ks = 0; ks < n_ksteps; ++ks) {
                 mbar_wait(&full_raw[s], phase);
-                float4* hi = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
-                float4* lo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + half_bytes);
-                for (uint32_t q0 = ct; q0 < item_chunks; q0 += TC_CONV_THREADS) {
-                    // 16-byte chunk q0 of the loaded part -> (plane, offset inside the plane)
-                    const uint32_t pl = q0 / plane_item_chunks, rem = q0 - pl * plane_item_chunks;
-                    const uint32_t q = pl * (plane_bytes / 16u) + skip_chunks + rem;
-                    const float4 x = hi[q];
-                    float4 h, l;
-                    h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
-                    l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y);
-                    l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
-                    hi[q] = h;
-                    lo[q] = l;
+                for (int sl = 0; sl < n_slots; ++sl) {
+                    float4* hi = reinterpret_cast<float4*>(base + (size_t)s * TC_STAGE + (size_t)sl * TC_SLOT);
+                    float4* lo = hi + (2 * TC_PLANE) / 16;
+#pragma unroll 4
+                    for (int q = ct; q < (2 * TC_PLANE) / 16; q += TC_CONV_THREADS) {
+                        const float4 x = hi[q];
+                        float4 h, l;
+                        if (a.rewrite_hi) {
+                            h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+                            hi[q] = h;
+                        } else {                                 // the tensor core ignores the low 13 mantissa bits
+                            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                        }
+                        l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y);
+                        l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
+                        lo[q] = l;
+                    }
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&full_conv[s]);
-                if (++s == a.n_stages) { s = 0; phase ^= 1u; }
+                if (++s == TC_STAGES) { s = 0; phase ^= 1u; }
             }
         }
     } else {
-        // ===== epilogue (warps 6..9): TMEM -> registers -> global, once per accumulation chain =====
+        // ===== epilogue (warps 8..15) =====
         // The tensor core adds into its FP32 accumulators with truncation, so the error of a chain grows
-        // linearly with the number of MMAs feeding one accumulator (~3e-8 per MMA, measured).  Chains are
-        // therefore cut after `chain_ksteps` stages and combined here with ordinary round-to-nearest FP32
-        // adds; the partial tile a later chain re-reads was written by this CTA moments ago (L2 hits).
+        // linearly with the number of MMAs feeding one accumulator (~3e-8 per MMA, measured on B200).  Chains
+        // are therefore cut after `chain_ksteps` stages; the partial tile is pulled out of TMEM (double
+        // buffered, so the next chain's MMAs overlap) and summed in registers with round-to-nearest FP32 adds.
+        // Thread = output row i of the tile and 64 of its 128 columns: 64 re + 64 im running sums.
+        reg_inc<208>();
         const int lane_grp = warp & 3;                          // TMEM lanes this warp may read
-        uint32_t acc_phase = 0;
-        for (int item = blockIdx.x, round = 0; item < n_items; item += gridDim.x, ++round) {
-            int f, mblk;
-            decode_item(item, round, a.n_mblk, f, mblk);
-            // Thread = output row i, columns n0 + [0, N).  Elements above the diagonal are stored twice (as is,
-            // and conjugated into the mirrored position -- lanes hold consecutive i, so those stores coalesce);
-            // nothing below the diagonal is used, which makes the result exactly Hermitian.
-            const int n0 = 128 * mblk, N = C - n0;
-            const int i = n0 + lane_grp * 32 + lane;
-            float2* __restrict__ fmat = a.acc + (size_t)f * C * C;
-            float2* __restrict__ orow = fmat + (size_t)i * C;
-            const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-            const int i_warp_min = n0 + lane_grp * 32;             // smallest row of this warp
-            for (int k0 = 0; k0 < n_ksteps; k0 += chain_ksteps) {
-                const float beta = k0 == 0 ? a.beta : 1.f;
-                mbar_wait(acc_full, acc_phase);
+        const int chalf = (warp - 8) >> 2;                      // which 64 columns
+        uint32_t chain = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int f, ti, tj;
+            decode_item(item, a.n_tiles, f, ti, tj);
+            float sr[64], si[64];
+#pragma unroll
+            for (int c = 0; c < 64; ++c) { sr[c] = 0.f; si[c] = 0.f; }
+            for (int k0 = 0; k0 < n_ksteps; k0 += chain_ksteps, ++chain) {
+                const uint32_t buf = chain & 1u;
+                mbar_wait(&acc_full[buf], (chain >> 1) & 1u);
                 tc_fence_after();
-                for (int c0 = 0; c0 < N; c0 += 16) {
-                    const int j0 = n0 + c0;
-                    if (j0 + 15 < i_warp_min) continue;            // chunk entirely below the diagonal (warp-uniform)
+                const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * 256u + (uint32_t)(chalf * 64);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
                     uint32_t vr[16], vi[16];
                     tmem_ld16(t_row + (uint32_t)c0, vr);
-                    tmem_ld16(t_row + (uint32_t)(N + c0), vi);
+                    tmem_ld16(t_row + 128u + (uint32_t)c0, vi);
                     tmem_ld_wait();
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) {
-                        const int j = j0 + jj;
-                        if (j < i) continue;
-                        float2 o = make_float2(__uint_as_float(vr[jj]) * a.alpha, __uint_as_float(vi[jj]) * a.alpha);
-                        float2* d0 = orow + j;
-                        if (beta != 0.f) {
-                            const float2 old0 = *d0;
-                            o.x += beta * old0.x; o.y += beta * old0.y;
-                        }
-                        if (j == i) o.y = 0.f;                      // auto-spectra are exactly real
-                        *d0 = o;
-                        if (j != i) fmat[(size_t)j * C + i] = make_float2(o.x, -o.y);
+                        sr[c0 + jj] += __uint_as_float(vr[jj]);
+                        si[c0 + jj] += __uint_as_float(vi[jj]);
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(acc_empty);
-                acc_phase ^= 1u;
+                mbar_arrive(&acc_empty[buf]);
+            }
+            // ---- store: elements on / above the diagonal as they are, plus their conjugates mirrored below it;
+            // nothing computed below the diagonal is used, so the result is exactly Hermitian.  A thread owns a
+            // row, so the mirrored stores (fixed j, lanes = consecutive i) coalesce as they are; the direct ones
+            // go through a per-warp 32 x 16 shared-memory transpose so that half-warps write 128-byte row pieces.
+            const int i0 = ti * 128 + lane_grp * 32;             // first row of this warp
+            const int i = i0 + lane;
+            const int jb = tj * 128 + chalf * 64;
+            float2* __restrict__ fmat = a.acc + (size_t)f * C * C;
+            float2* stg = staging + (warp - 8) * (32 * 16);
+            const bool diag_tile = ti == tj;
+            if (a.store_mode == 0) {
+                float2* __restrict__ orow = fmat + (size_t)i * C;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    const int j = jb + c;
+                    if (diag_tile && j < i) continue;
+                    float2 o = make_float2(sr[c] * a.alpha, si[c] * a.alpha);
+                    if (a.beta != 0.f) {
+                        const float2 old0 = orow[j];
+                        o.x += a.beta * old0.x; o.y += a.beta * old0.y;
+                    }
+                    if (j == i) o.y = 0.f;
+                    orow[j] = o;
+                    if (j != i) fmat[(size_t)j * C + i] = make_float2(o.x, -o.y);
+                }
+                continue;
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                if (diag_tile && jb + c0 + 15 < i0) continue;    // chunk entirely below the diagonal (warp-uniform)
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int j = jb + c0 + jj;
+                    float2 o = make_float2(sr[c0 + jj] * a.alpha, si[c0 + jj] * a.alpha);
+                    if (a.beta != 0.f && (!diag_tile || j >= i)) {
+                        const float2 old0 = fmat[(size_t)i * C + j];
+                        o.x += a.beta * old0.x; o.y += a.beta * old0.y;
+                    }
+                    if (j == i) o.y = 0.f;                      // auto-spectra are exactly real
+                    stg[lane * 16 + (jj ^ (lane & 15))] = o;
+                    if (!diag_tile || j > i) fmat[(size_t)j * C + i] = make_float2(o.x, -o.y);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 16; ++it) {
+                    const int r = 2 * it + (lane >> 4), cc = lane & 15;
+                    const int ii = i0 + r, j = jb + c0 + cc;
+                    const float2 o = stg[r * 16 + (cc ^ (r & 15))];
+                    if (!diag_tile || j >= ii) fmat[(size_t)ii * C + j] = o;
+                }
+                __syncwarp();
             }
         }
     }
@@ -364,7 +435,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+        tmem_dealloc(tmem_base, 512u);
     }
 }
 
@@ -415,22 +486,19 @@ int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream) {
 
     TcArgs a;
     a.n_rows = d.n_rows; a.n_freq = d.n_freq; a.n_chan = C;
-    a.n_mblk = (C + 127) / 128;
-    a.cb_stride = C / 32;
+    a.n_tiles = C == 256 ? 3 : 1;
     a.alpha = d.alpha; a.beta = d.beta;
     a.acc = reinterpret_cast<float2*>(d.acc);
-    a.tmem_cols = 32;
-    while (a.tmem_cols < 2 * C) a.tmem_cols <<= 1;
     // accumulation-chain length in rows (multiple of TC_KC); SPYB_TC_CHAIN_ROWS overrides for experiments
-    int chain_rows = 128;
+    int chain_rows = 64;
     if (const char* e = getenv("SPYB_TC_CHAIN_ROWS")) chain_rows = atoi(e);
     if (chain_rows < TC_KC) chain_rows = TC_KC;
     a.chain_ksteps = chain_rows / TC_KC;
-    const size_t stage_bytes = (size_t)4 * a.cb_stride * TC_KC * 128;
-    a.n_stages = (int)((200 * 1024) / stage_bytes);
-    if (a.n_stages > 8) a.n_stages = 8;
-    if (a.n_stages < 2) return fail("csd_tc: stage does not fit shared memory");
-    const size_t smem = 1024 + (size_t)a.n_stages * stage_bytes + (3 * a.n_stages + 2) * 8 + 16;
+    a.store_mode = 1;
+    if (const char* e = getenv("SPYB_TC_STORE")) a.store_mode = atoi(e);
+    a.rewrite_hi = 1;
+    if (const char* e = getenv("SPYB_TC_REWRITE_HI")) a.rewrite_hi = atoi(e) != 0;
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2);
 
     static bool configured = false;
     if (!configured) {
@@ -440,9 +508,8 @@ int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream) {
     int dev = 0, n_sm = 148;
     SPYB_CUDA(cudaGetDevice(&dev));
     SPYB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int n_items = d.n_freq * a.n_mblk;
-    int grid = n_items < n_sm ? n_items : n_sm;
-    if (a.n_mblk == 2) grid &= ~1;      // decode_item() pairs the two block rows of a frequency within a round
+    const int n_items = d.n_freq * a.n_tiles;
+    const int grid = n_items < n_sm ? n_items : n_sm;
     csd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, a);
     SPYB_LAUNCH_CHECK("csd_tc_kernel");
     count_launch();

@@ -113,6 +113,35 @@ int spyb_csd_accumulate_planar(const float* planes, long long sx_f, long long sx
 int spyb_csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind,
                        void* out, void* stream);
 
+/*
+ * Whole-trial detrend: out = x - (mean [+ slope * t]) per channel, float32 (scipy.signal.detrend along time as
+ * called at syncopy/specest/compRoutines.py:582-585, 751-753).  polyremoval: -1 copy, 0 de-mean, 1 linear.
+ */
+int spyb_detrend(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, int polyremoval,
+                 float* out, long long out_trial_stride, void* stream);
+
+/*
+ * Wavelet / superlet transform as FFT convolution with per-scale products of powers:
+ *     z[trial][n][s][c] = prod_{j < n_fac[s]} ( conv_same(x[trial][:, c], psi_{s,j})[n] ) ^ expo[s][j]
+ * Replaces: syncopy/specest/wavelets/transform.py:88-108 (`cwt_time`; one factor, exponent 1),
+ *           syncopy/specest/superlet.py:108-198, 321-365 (`multiplicativeSLT`, `FASLT`, `cwtSL`) and the output
+ *           conversion of syncopy/specest/compRoutines.py:593-595, 760-762.
+ *   xspec   complex64 [n_trials][n_dft/2+1][n_chan]: one-sided FFT_{n_dft} of the zero-padded (detrended) trials,
+ *           as spyb_mtmfft writes it with a unit taper, scale 1 and nfft = n_dft
+ *   kern    complex64 [n_scales][max_fac][n_dft] = FFT_{n_dft}(h_{s,j}) / n_dft with h[d mod n_dft] = psi[d + (M-1)/2]
+ *           (psi sampled by the caller in float64 exactly as the reference does; n_dft a power of two <= 16384,
+ *           >= n_samples + the kernel's half support)
+ *   expo    float32 [n_scales][max_fac] exponents (principal-branch complex power; 1 = none)
+ *   n_fac   int32 [n_scales] number of factors in use
+ *   out     [n_trials][n_time][n_scales][n_chan] float32 or complex64 by out_kind; rows n = 0 .. n_time-1
+ */
+int spyb_cwt(const void* xspec, int n_trials, int n_chan, int n_dft, const void* kern, const float* expo,
+             const int* n_fac, int n_scales, int max_fac, int n_time, int out_kind, void* out, void* stream);
+
+/* dst[t][i][:] = src[t][idx[i]][:], rows of row_elems float32 (time post-selection, compRoutines.py:593) */
+int spyb_gather_rows(const float* src, int n_trials, long long src_trial_stride, const int* idx, int n_idx,
+                     long long row_elems, float* dst, void* stream);
+
 /* x *= s on n float32 (trial mean `/= nTrials`, computational_routine.py:1030-1032) */
 int spyb_scale(float* x, long long n, float s, void* stream);
 

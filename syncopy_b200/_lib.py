@@ -35,6 +35,9 @@ PROTOTYPES = {
     "spyb_csd_planar_supported": (_i, [_i, _ll, _ll]),
     "spyb_csd_accumulate_planar": (_i, [_vp, _ll, _ll, _i, _i, _i, _f, _f, _vp, _vp]),
     "spyb_csd_normalize": (_i, [_vp, _ll, _i, _f, _i, _vp, _vp]),
+    "spyb_detrend": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _ll, _vp]),
+    "spyb_cwt": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "spyb_gather_rows": (_i, [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp]),
     "spyb_scale": (_i, [_vp, _ll, _f, _vp]),
 }
 

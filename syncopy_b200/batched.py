@@ -213,3 +213,48 @@ def coherence(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper
         n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group)
     coh = eng.csd_normalize(res.csd_sum[None], output=output, pre_scale=1.0 / n_total)
     return _finish(coh, to_host, out_host), res.freqs
+
+
+def _conv_transform(eng, trials, plan_key, make_taps, polyremoval, output, to_host, trial_chunk):
+    x = _device_trials(eng, trials)
+    B, n_sig, n_chan = x.shape
+    taps, expo = make_taps()
+    plan = eng.conv_plan(plan_key, n_sig, taps, expo)
+    kind_complex = hm.out_kind(output) == 2
+    out = torch.empty((B, n_sig, 1, plan["n_scales"], n_chan),
+                      dtype=torch.complex64 if kind_complex else torch.float32, device=eng.tdev)
+    chunk = max(1, int(trial_chunk))
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        xd = eng.detrend(x[b0:b0 + nb], hm.polyremoval_code(polyremoval))
+        eng.cwt(xd, plan, output=output, out=out[b0:b0 + nb].view(nb, n_sig, plan["n_scales"], n_chan))
+    return out.cpu().numpy() if to_host else out
+
+
+def wavelet(trials, samplerate, scales, wavelet, polyremoval=0, output="pow", to_host=False, engine=None,
+            trial_chunk=32):
+    """
+    All-trials `wavelet_cF` (syncopy/specest/compRoutines.py:482-595) for `toi='all'`:
+    [nTrials, nTime, 1, nScales, nChannels]; `wavelet` is any callable (t, s) -> psi (e.g. hostmath.Morlet()).
+    """
+    from .compute_functions import _plan_key
+    eng = engine or get_engine()
+    scales = np.asarray(scales, dtype=np.float64)
+    dt = 1.0 / samplerate
+    key = ("cwt", _plan_key(wavelet), scales.tobytes(), dt)
+    return _conv_transform(eng, trials, key,
+                           lambda: ([[hm.cwt_taps(wavelet, s, dt)] for s in scales], [[1.0] for _ in scales]),
+                           polyremoval, output, to_host, trial_chunk)
+
+
+def superlet(trials, samplerate, scales, order_max, order_min=1, c_1=3, adaptive=False, polyremoval=0,
+             output="pow", to_host=False, engine=None, trial_chunk=32):
+    """All-trials `superlet_cF` (syncopy/specest/compRoutines.py:654-762) for `toi='all'`."""
+    from .compute_functions import superlet_tables
+    eng = engine or get_engine()
+    scales = np.asarray(scales, dtype=np.float64)
+    dt = 1.0 / samplerate
+    kw = dict(order_max=order_max, order_min=order_min, c_1=c_1, adaptive=adaptive)
+    key = ("slt", scales.tobytes(), dt, tuple(sorted(kw.items())))
+    return _conv_transform(eng, trials, key, lambda: superlet_tables(scales, dt, **kw), polyremoval, output,
+                           to_host, trial_chunk)

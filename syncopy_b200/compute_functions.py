@@ -8,6 +8,8 @@ the arithmetic executed by libspyb200 on the GPU.
     cross_spectra_cF            <- syncopy/connectivity/ST_compRoutines.py:268-424
     spectral_dyadic_product_cF  <- syncopy/connectivity/ST_compRoutines.py:29-117
     normalize_csd_cF            <- syncopy/connectivity/AV_compRoutines.py:35-112
+    wavelet_cF                  <- syncopy/specest/compRoutines.py:482-595
+    superlet_cF                 <- syncopy/specest/compRoutines.py:654-762
 
 Each takes one trial as a host `ndarray` and returns a new host `ndarray`
 (+ metadata dict where the reference returns one), so it can be bound with
@@ -207,3 +209,90 @@ def normalize_csd_cF(csd_av_dat, output="abs", chunkShape=None, noCompute=False)
     eng = get_engine()
     x = eng.to_device(np.ascontiguousarray(csd_av_dat, dtype=np.complex64), dtype=torch.complex64)
     return eng.csd_normalize(x, output=output).cpu().numpy()
+
+
+# ---------------------------------------------------------------------------
+# freqanalysis: wavelet / superlet
+# ---------------------------------------------------------------------------
+
+def _plan_key(obj):
+    """Hashable identity of a wavelet object (class name + public attributes)."""
+    attrs = tuple(sorted((k, repr(v)) for k, v in vars(obj).items())) if hasattr(obj, "__dict__") else repr(obj)
+    return (type(obj).__name__, attrs)
+
+
+def _time_rows(sel, n):
+    """Row indices selected by a slice / index array / list out of n rows, or None for 'all rows in order'."""
+    if isinstance(sel, slice):
+        start, stop, step = sel.indices(n)
+        if (start, stop, step) == (0, n, 1):
+            return None
+        return np.arange(start, stop, step, dtype=np.int32)
+    idx = np.asarray(sel)
+    if idx.dtype == bool:
+        idx = np.flatnonzero(idx)
+    return np.where(idx < 0, idx + n, idx).astype(np.int32)
+
+
+def _conv_transform_cF(trl_dat, preselect, postselect, toi, timeAxis, polyremoval, output, noCompute,
+                       n_scales, plan_key, make_taps):
+    dat = _as_time_major(trl_dat, timeAxis)
+    n_time = toi.size if isinstance(toi, np.ndarray) else dat.shape[0]
+    out_shape = (n_time, 1, n_scales, dat.shape[1])
+    if noCompute:
+        return out_shape, hm.spectralDTypes[output]
+    eng = get_engine()
+    x = eng.detrend(_trial_to_device(eng, dat), hm.polyremoval_code(polyremoval))
+    rows_in = _time_rows(preselect, dat.shape[0])
+    if rows_in is not None:
+        if rows_in.size and not np.array_equal(rows_in, np.arange(rows_in[0], rows_in[0] + rows_in.size)):
+            raise ValueError("wavelet / superlet: `preselect` must be a contiguous sample range")
+        x = x[:, int(rows_in[0]):int(rows_in[0]) + rows_in.size, :] if rows_in.size else x[:, :0, :]
+    n_sel = x.shape[1]
+    taps, expo = make_taps()
+    plan = eng.conv_plan(plan_key, n_sel, taps, expo)
+    spec = eng.cwt(x, plan, output=output)                       # [1, n_sel, nScales, C]
+    rows_out = _time_rows(postselect, n_sel)
+    if rows_out is not None:
+        spec = eng.gather_rows(spec, rows_out)
+    return spec[0].cpu().numpy()[:, None, :, :]
+
+
+def wavelet_cF(trl_dat, preselect, postselect, toi=None, timeAxis=0, polyremoval=0, output="pow",
+               noCompute=False, chunkShape=None, method_kwargs=None):
+    scales = np.asarray(method_kwargs["scales"], dtype=np.float64)
+    wav = method_kwargs["wavelet"]
+    dt = 1.0 / method_kwargs["samplerate"]
+
+    def make_taps():
+        return [[hm.cwt_taps(wav, s, dt)] for s in scales], [[1.0] for _ in scales]
+
+    key = ("cwt", _plan_key(wav), scales.tobytes(), dt)
+    return _conv_transform_cF(trl_dat, preselect, postselect, toi, timeAxis, polyremoval, output, noCompute,
+                              scales.size, key, make_taps)
+
+
+def superlet_cF(trl_dat, preselect, postselect, toi=None, timeAxis=0, polyremoval=0, output="pow",
+                noCompute=False, chunkShape=None, method_kwargs=None):
+    scales = np.asarray(method_kwargs["scales"], dtype=np.float64)
+    dt = 1.0 / method_kwargs["samplerate"]
+    kw = dict(order_max=method_kwargs["order_max"], order_min=method_kwargs.get("order_min", 1),
+              c_1=method_kwargs.get("c_1", 3), adaptive=method_kwargs.get("adaptive", False))
+
+    def make_taps():
+        return superlet_tables(scales, dt, **kw)
+
+    key = ("slt", scales.tobytes(), dt, tuple(sorted(kw.items())))
+    return _conv_transform_cF(trl_dat, preselect, postselect, toi, timeAxis, polyremoval, output, noCompute,
+                              scales.size, key, make_taps)
+
+
+def superlet_tables(scales, dt, order_max, order_min=1, c_1=3, adaptive=False):
+    """(taps[s][j], exponents[s][j]) of a superlet transform; zero exponents (z**0 = 1) are dropped."""
+    factors = hm.superlet_factors(scales, order_max, order_min, c_1, adaptive)
+    taps, expo = [], []
+    for s, fl in zip(scales, factors):
+        fl = [(c, a) for (c, a) in fl if a != 0.0] or [fl[0]]
+        taps.append([hm.superlet_taps(c, s, dt) for c, _ in fl])
+        expo.append([a for _, a in fl])
+    return taps, expo

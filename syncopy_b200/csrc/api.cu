@@ -114,6 +114,27 @@ int spyb_csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_s
     return csd_normalize(csd, n_mat, n_chan, pre_scale, out_kind, out, static_cast<cudaStream_t>(stream));
 }
 
+int spyb_detrend(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, int polyremoval,
+                 float* out, long long out_trial_stride, void* stream) {
+    return detrend(x, n_trials, trial_stride, n_samples, n_chan, polyremoval, out, out_trial_stride,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int spyb_cwt(const void* xspec, int n_trials, int n_chan, int n_dft, const void* kern, const float* expo,
+             const int* n_fac, int n_scales, int max_fac, int n_time, int out_kind, void* out, void* stream) {
+    if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
+    CwtDesc d;
+    d.xspec = xspec; d.n_trials = n_trials; d.n_chan = n_chan; d.n_dft = n_dft;
+    d.kern = kern; d.expo = expo; d.n_fac = n_fac; d.n_scales = n_scales; d.max_fac = max_fac;
+    d.n_time = n_time; d.out_kind = out_kind; d.out = out;
+    return cwt_factors(d, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_gather_rows(const float* src, int n_trials, long long src_trial_stride, const int* idx, int n_idx,
+                     long long row_elems, float* dst, void* stream) {
+    return gather_rows(src, n_trials, src_trial_stride, idx, n_idx, row_elems, dst, static_cast<cudaStream_t>(stream));
+}
+
 int spyb_scale(float* x, long long n, float s, void* stream) {
     return scale_inplace(x, n, s, static_cast<cudaStream_t>(stream));
 }

@@ -181,43 +181,119 @@ __device__ __forceinline__ float2 csqrt_principal(float2 z) {
     return make_float2(fabsf(im), copysignf(re, z.y));
 }
 
-__global__ void __launch_bounds__(256) csd_normalize_kernel(const float2* __restrict__ csd, int n_chan,
-                                                            long long n_mat, float pre_scale, int out_kind,
-                                                            void* __restrict__ out) {
-    // one block per (matrix, row i); threads run along j
-    const long long row = blockIdx.x;
-    const long long mat = row / n_chan;
-    const int i = (int)(row % n_chan);
-    if (mat >= n_mat) return;
-    const float2* __restrict__ M = csd + mat * n_chan * n_chan;
-    float2 dii = M[(long long)i * n_chan + i];
-    dii.x *= pre_scale; dii.y *= pre_scale;
-    for (int j = threadIdx.x; j < n_chan; j += blockDim.x) {
-        float2 djj = M[(long long)j * n_chan + j];
-        djj.x *= pre_scale; djj.y *= pre_scale;
-        float2 cij = M[(long long)i * n_chan + j];
-        cij.x *= pre_scale; cij.y *= pre_scale;
-        const float2 den = csqrt_principal(cmul(dii, djj));
-        // complex division cij / den
-        const float d2 = den.x * den.x + den.y * den.y;
-        const float2 coh = make_float2((cij.x * den.x + cij.y * den.y) / d2, (cij.y * den.x - cij.x * den.y) / d2);
-        const long long o = row * n_chan + j;
-        if (out_kind == OUT_FOURIER) reinterpret_cast<float2*>(out)[o] = coh;
-        else reinterpret_cast<float*>(out)[o] = convert_real(coh, out_kind);
+// One block = NORM_ROWS rows of one matrix.  The diagonal is staged once per block: when it is real and
+// non-negative (every CSD this library produces; auto-spectra are exactly real) 1/sqrt(pre*C_jj) is kept in
+// shared memory and an element costs two multiplies; otherwise the general complex square root of the
+// reference (np.sqrt of the complex product, csd.py:161-170) is taken.  Rows are read / written as whole
+// 128-byte lines (two complex per thread and step).
+constexpr int NORM_ROWS = 8;
+
+template <int KIND>
+__device__ __forceinline__ void norm_store(void* __restrict__ out, long long o, float2 c0, float2 c1) {
+    if (KIND == OUT_FOURIER) {
+        reinterpret_cast<float4*>(out)[o >> 1] = make_float4(c0.x, c0.y, c1.x, c1.y);
+    } else {
+        float r0, r1;
+        if (KIND == OUT_ABS) { r0 = sqrtf(c0.x * c0.x + c0.y * c0.y); r1 = sqrtf(c1.x * c1.x + c1.y * c1.y); }
+        else { r0 = convert_real(c0, KIND); r1 = convert_real(c1, KIND); }
+        reinterpret_cast<float2*>(out)[o >> 1] = make_float2(r0, r1);
     }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) csd_normalize_kernel(const float2* __restrict__ csd, int n_chan,
+                                                            long long n_mat, float pre_scale,
+                                                            void* __restrict__ out) {
+    extern __shared__ float2 s_diag[];           // [n_chan] scaled diagonal, then [n_chan] floats 1/sqrt
+    float* s_rs = reinterpret_cast<float*>(s_diag + n_chan);
+    __shared__ int s_general;
+    const int row_blocks = (n_chan + NORM_ROWS - 1) / NORM_ROWS;
+    const long long mat = blockIdx.x / row_blocks;
+    const int i0 = (int)(blockIdx.x % row_blocks) * NORM_ROWS;
+    const float2* __restrict__ M = csd + mat * n_chan * n_chan;
+    if (threadIdx.x == 0) s_general = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_chan; j += blockDim.x) {
+        float2 d = M[(long long)j * n_chan + j];
+        d.x *= pre_scale; d.y *= pre_scale;
+        s_diag[j] = d;
+        s_rs[j] = rsqrtf(d.x);
+        if (d.y != 0.f || !(d.x > 0.f)) s_general = 1;
+    }
+    __syncthreads();
+    const bool general = s_general != 0;
+    const bool vec = (n_chan % 2) == 0;
+    for (int r = 0; r < NORM_ROWS; ++r) {
+        const int i = i0 + r;
+        if (i >= n_chan) break;
+        const float2 dii = s_diag[i];
+        const float rsi = s_rs[i] * pre_scale;
+        const long long row = (mat * n_chan + i) * n_chan;
+        for (int j = 2 * threadIdx.x; j < n_chan; j += 2 * blockDim.x) {
+            float2 c[2];
+            const bool two = j + 1 < n_chan;
+            if (vec) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(csd + row + j));
+                c[0] = make_float2(v.x, v.y); c[1] = make_float2(v.z, v.w);
+            } else {
+                c[0] = __ldg(csd + row + j);
+                c[1] = two ? __ldg(csd + row + j + 1) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int jj = j + e < n_chan ? j + e : j;
+                if (!general) {
+                    const float w = rsi * s_rs[jj];
+                    c[e].x *= w; c[e].y *= w;
+                } else {
+                    const float2 num = make_float2(c[e].x * pre_scale, c[e].y * pre_scale);
+                    const float2 den = csqrt_principal(cmul(dii, s_diag[jj]));
+                    const float d2 = den.x * den.x + den.y * den.y;
+                    c[e] = make_float2((num.x * den.x + num.y * den.y) / d2, (num.y * den.x - num.x * den.y) / d2);
+                }
+            }
+            if (vec) {
+                norm_store<KIND>(out, row + j, c[0], c[1]);
+            } else {
+                for (int e = 0; e < (two ? 2 : 1); ++e) {
+                    if (KIND == OUT_FOURIER) reinterpret_cast<float2*>(out)[row + j + e] = c[e];
+                    else reinterpret_cast<float*>(out)[row + j + e] =
+                        KIND == OUT_ABS ? sqrtf(c[e].x * c[e].x + c[e].y * c[e].y) : convert_real(c[e], KIND);
+                }
+            }
+        }
+    }
+}
+
+template <int KIND>
+static int launch_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, void* out,
+                            cudaStream_t stream) {
+    const long long blocks = n_mat * ((n_chan + NORM_ROWS - 1) / NORM_ROWS);
+    if (blocks > 2147483647LL) return fail("csd_normalize: too many blocks (%lld)", blocks);
+    const int threads = n_chan >= 512 ? 256 : (n_chan >= 256 ? 128 : 64);
+    const size_t smem = (size_t)n_chan * (sizeof(float2) + sizeof(float));
+    if (smem > 48 * 1024) return fail("csd_normalize: more than 4096 channels are not supported");
+    csd_normalize_kernel<KIND><<<(unsigned)blocks, threads, smem, stream>>>(
+        reinterpret_cast<const float2*>(csd), n_chan, n_mat, pre_scale, out);
+    SPYB_LAUNCH_CHECK("csd_normalize_kernel");
+    count_launch();
+    return 0;
 }
 
 int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind, void* out,
                   cudaStream_t stream) {
     if (n_mat <= 0 || n_chan <= 0) return 0;
-    const long long rows = n_mat * n_chan;
-    if (rows > 2147483647LL) return fail("csd_normalize: too many rows (%lld)", rows);
-    const int threads = n_chan >= 256 ? 256 : (n_chan >= 128 ? 128 : 64);
-    csd_normalize_kernel<<<(unsigned)rows, threads, 0, stream>>>(reinterpret_cast<const float2*>(csd), n_chan,
-                                                                n_mat, pre_scale, out_kind, out);
-    SPYB_LAUNCH_CHECK("csd_normalize_kernel");
-    count_launch();
-    return 0;
+    switch (out_kind) {
+        case OUT_POW:     return launch_normalize<OUT_POW>(csd, n_mat, n_chan, pre_scale, out, stream);
+        case OUT_ABS:     return launch_normalize<OUT_ABS>(csd, n_mat, n_chan, pre_scale, out, stream);
+        case OUT_FOURIER: return launch_normalize<OUT_FOURIER>(csd, n_mat, n_chan, pre_scale, out, stream);
+        case OUT_REAL:    return launch_normalize<OUT_REAL>(csd, n_mat, n_chan, pre_scale, out, stream);
+        case OUT_IMAG:    return launch_normalize<OUT_IMAG>(csd, n_mat, n_chan, pre_scale, out, stream);
+        case OUT_ANGLE:   return launch_normalize<OUT_ANGLE>(csd, n_mat, n_chan, pre_scale, out, stream);
+        case OUT_ABSREAL: return launch_normalize<OUT_ABSREAL>(csd, n_mat, n_chan, pre_scale, out, stream);
+        case OUT_ABSIMAG: return launch_normalize<OUT_ABSIMAG>(csd, n_mat, n_chan, pre_scale, out, stream);
+        default:          return fail("bad out_kind %d", out_kind);
+    }
 }
 
 // in-place scale of a float buffer (trial mean: computational_routine.py:1030-1032)

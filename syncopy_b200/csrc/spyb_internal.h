@@ -50,6 +50,23 @@ struct CsdPlanarDesc {
 };
 bool csd_tc_supported(int n_chan, long long sx_f, long long sx_r);
 int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream);
+// Wavelet / superlet transforms as FFT convolutions (cwt.cu)
+struct CwtDesc {
+    const void* xspec = nullptr;     // device complex64 [trial][L/2+1][chan], spectra of the zero-padded trials
+    int n_trials = 0, n_chan = 0, n_dft = 0;
+    const void* kern = nullptr;      // device complex64 [scale][max_fac][L] = FFT_L(h) / L
+    const float* expo = nullptr;     // device [scale][max_fac]
+    const int* n_fac = nullptr;      // device [scale]
+    int n_scales = 0, max_fac = 1;
+    int n_time = 0, out_kind = 0;
+    void* out = nullptr;             // device [trial][n_time][scale][chan]
+};
+int cwt_factors(const CwtDesc& d, cudaStream_t stream);
+int detrend(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, int polyremoval,
+            float* out, long long out_trial_stride, cudaStream_t stream);
+int gather_rows(const float* src, int n_trials, long long src_trial_stride, const int* idx, int n_idx,
+                long long row_elems, float* dst, cudaStream_t stream);
+
 int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind, void* out,
                   cudaStream_t stream);
 int scale_inplace(float* x, long long n, float s, cudaStream_t stream);

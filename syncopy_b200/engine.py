@@ -193,6 +193,76 @@ class Engine:
                                                out.data_ptr(), self.stream()))
         return out
 
+    # ------------------------------------------------------------------ K5 / K6: wavelets, superlets
+    def detrend(self, x, polyremoval):
+        """Whole-trial detrend of x [B, N, C] (new tensor); polyremoval -1 / 0 / 1."""
+        tstride = _trial_layout(x)
+        B, N, Cn = x.shape
+        out = torch.empty((B, N, Cn), dtype=torch.float32, device=self.tdev)
+        _lib.check(self.lib.spyb_detrend(x.data_ptr(), B, tstride, N, Cn, int(polyremoval), out.data_ptr(),
+                                         N * Cn, self.stream()))
+        return out
+
+    def conv_plan(self, key, n_samples, taps_per_scale, exponents):
+        """
+        Device tables of a 'same'-convolution transform: `taps_per_scale[s][j]` are the sampled kernels of scale
+        s (float64 / complex128 host arrays), `exponents[s][j]` their powers.  Cached under `key`.
+        """
+        key = ("conv", key, int(n_samples))
+        if key not in self._tables:
+            flat = [t for tl in taps_per_scale for t in tl]
+            L = hm.conv_same_length(n_samples, flat)
+            if L > self.lib.spyb_max_fft_len(1):
+                raise _lib.SpybError(
+                    f"wavelet transform of {n_samples} samples needs a circular length of {L} > "
+                    f"{self.lib.spyb_max_fft_len(1)} (the shared-memory FFT engine's limit)")
+            nS = len(taps_per_scale)
+            max_fac = max(len(tl) for tl in taps_per_scale)
+            kern = np.zeros((nS, max_fac, L), dtype=np.complex64)
+            expo = np.ones((nS, max_fac), dtype=np.float32)
+            nfac = np.zeros(nS, dtype=np.int32)
+            for si, (tl, el) in enumerate(zip(taps_per_scale, exponents)):
+                nfac[si] = len(tl)
+                for j, (taps, e) in enumerate(zip(tl, el)):
+                    kern[si, j] = hm.conv_same_spectrum(taps, n_samples, L)
+                    expo[si, j] = e
+            self._tables[key] = dict(L=L, n_scales=nS, max_fac=max_fac,
+                                     kern=torch.from_numpy(kern).to(self.tdev),
+                                     expo=torch.from_numpy(expo).to(self.tdev),
+                                     nfac=torch.from_numpy(nfac).to(self.tdev),
+                                     ones=torch.ones((1, n_samples), dtype=torch.float32, device=self.tdev))
+        return self._tables[key]
+
+    def cwt(self, x, plan, output="fourier", out=None):
+        """
+        x [B, N, C] float32 (already detrended / time-selected) -> [B, N, nScales, C]: per scale the product of
+        powers of 'same' convolutions described by `plan` (see `conv_plan`).
+        """
+        B, N, Cn = x.shape
+        L, nS = plan["L"], plan["n_scales"]
+        xspec = self.mtmfft(x, plan["ones"], L, 1.0, polyremoval=-1, output="fourier", keeptapers=True)
+        kind = hm.out_kind(output)
+        dt = _CDTYPE[kind == 2]
+        if out is None:
+            out = torch.empty((B, N, nS, Cn), dtype=dt, device=self.tdev)
+        assert out.is_contiguous() and out.dtype == dt and tuple(out.shape) == (B, N, nS, Cn)
+        _lib.check(self.lib.spyb_cwt(xspec.data_ptr(), B, Cn, L, plan["kern"].data_ptr(), plan["expo"].data_ptr(),
+                                     plan["nfac"].data_ptr(), nS, plan["max_fac"], N, kind, out.data_ptr(),
+                                     self.stream()))
+        return out
+
+    def gather_rows(self, src, idx):
+        """src [B, R, ...] float32 / complex64 -> [B, len(idx), ...] (rows idx of every trial)."""
+        assert src.is_contiguous()
+        B, R = src.shape[:2]
+        tidx = self.index_table(idx)
+        out = torch.empty((B, tidx.numel()) + tuple(src.shape[2:]), dtype=src.dtype, device=self.tdev)
+        words = (2 if src.dtype == torch.complex64 else 1)
+        row = int(np.prod(src.shape[2:])) * words
+        _lib.check(self.lib.spyb_gather_rows(src.data_ptr(), B, R * row, tidx.data_ptr(), tidx.numel(), row,
+                                             out.data_ptr(), self.stream()))
+        return out
+
     def scale_(self, t, s):
         """In-place t *= s for float32 / complex64 CUDA tensors."""
         assert t.is_cuda and t.is_contiguous()

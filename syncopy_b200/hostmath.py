@@ -95,3 +95,139 @@ def polyremoval_code(polyremoval):
     if polyremoval == 1:
         return 1
     return -1
+
+
+# ---------------------------------------------------------------------------
+# wavelet / superlet kernels: sampled on the host in float64 exactly as the
+# reference samples them, then handed to the GPU as convolution spectra
+#   syncopy/specest/wavelets/wavelets.py:13-312   Morlet / Paul / DOG (time forms)
+#   syncopy/specest/wavelets/transform.py:96-103  support + normalisation of cwt_time
+#   syncopy/specest/superlet.py:255-299, 355-380  MorletSL, support + normalisation of cwtSL
+#   syncopy/specest/superlet.py:108-198, 383-401  order / exponent bookkeeping
+# ---------------------------------------------------------------------------
+
+class Morlet:
+    """Complete Morlet wavelet pi^-1/4 (exp(i w0 x) - exp(-w0^2/2)) exp(-x^2/2), x = t/s."""
+
+    def __init__(self, w0=6):
+        self.w0 = w0
+
+    def __call__(self, t, s=1.0):
+        x = t / s
+        return (np.exp(1j * self.w0 * x) - np.exp(-0.5 * self.w0 ** 2)) * (np.pi ** -0.25 * np.exp(-0.5 * x ** 2))
+
+    def fourier_period(self, s):
+        return 4 * np.pi * s / (self.w0 + (2 + self.w0 ** 2) ** 0.5)
+
+    def scale_from_period(self, period):
+        return period * (np.sqrt(self.w0 ** 2 + 2) + self.w0) / (4.0 * np.pi)
+
+
+class Paul:
+    """Paul wavelet of order m."""
+
+    def __init__(self, m=4):
+        self.m = m
+
+    def __call__(self, t, s=1.0):
+        from scipy.special import factorial
+        m, x = self.m, t / s
+        const = (2 ** m * 1j ** m * factorial(m)) / (np.pi * factorial(2 * m)) ** 0.5
+        return const * (1 - 1j * x) ** -(m + 1)
+
+    def fourier_period(self, s):
+        return 4 * np.pi * s / (2 * self.m + 1)
+
+    def scale_from_period(self, period):
+        return period * (2 * self.m + 1) / (4 * np.pi)
+
+
+class DOG:
+    """m-th derivative of a Gaussian (real valued)."""
+
+    def __init__(self, m=2):
+        self.m = m
+
+    def __call__(self, t, s=1.0):
+        from scipy.special import gamma, hermitenorm
+        m, x = self.m, t / s
+        return (-1) ** (m + 1) / gamma(m + 0.5) ** 0.5 * hermitenorm(m)(x) * np.exp(-x ** 2 / 2)
+
+    def fourier_period(self, s):
+        return 2 * np.pi * s / (self.m + 0.5) ** 0.5
+
+    def scale_from_period(self, period):
+        return period * np.sqrt(self.m + 0.5) / (2 * np.pi)
+
+
+def support_times(M, dt):
+    return np.arange((-M + 1) / 2.0, (M + 1) / 2.0) * dt
+
+
+def cwt_taps(wavelet, scale, dt):
+    """Sampled, normalised CWT kernel of one scale; `wavelet` is any callable (t, s) -> psi."""
+    t = support_times(10 * scale / dt, dt)
+    return (dt ** 0.5 / (scale * 8 * np.pi)) * np.asarray(wavelet(t, scale))
+
+
+def superlet_taps(c_i, scale, dt, k_sd=5):
+    """Sampled, normalised Morlet of `c_i` cycles as `cwtSL` builds it."""
+    t = support_times(10 * scale * c_i / dt, dt)
+    ts = t / scale
+    B_c = k_sd / (scale * c_i * (2 * np.pi) ** 1.5)
+    psi = B_c * np.exp(1j * ts) * np.exp(-0.5 * (k_sd * ts / (2 * np.pi * c_i)) ** 2)
+    return (dt ** 0.5 / (4 * np.pi)) * psi
+
+
+def superlet_factors(scales, order_max, order_min=1, c_1=3, adaptive=False):
+    """
+    Per scale the list of (cycle count, exponent) whose powers the superlet multiplies:
+    multiplicative: every order with exponent 1/nOrders; FASLT: the fractional-order bookkeeping of the
+    reference (first wavelet set on every scale, later sets from index `last` on, `alphas = orders % floor`).
+    """
+    scales = np.asarray(scales, dtype=np.float64)
+    if not adaptive:
+        cycles = c_1 * np.arange(order_min, order_max + 1)
+        n_ord = order_max + 1 - order_min
+        return [[(int(c), 1.0 / n_ord) for c in cycles] for _ in scales]
+    fois = 1 / (2 * np.pi * scales)
+    orders = order_min + (order_max - order_min) * (fois - fois[0]) / (fois[-1] - fois[0])
+    orders_int = np.int32(np.floor(orders))
+    cycles = c_1 * np.unique(orders_int)
+    exponents = 1 / (orders - order_min + 1)
+    jumps = np.where(np.diff(orders_int))[0]
+    alphas = orders % orders_int
+    if len(cycles) != len(jumps) + 1:
+        raise ValueError("superlet: scales must be ordered high -> low for the adaptive transform")
+    factors = [[(int(cycles[0]), float(exponents[i]))] for i in range(scales.size)]
+    last = 1
+    for k, jump in enumerate(jumps):
+        for i in range(last, scales.size):
+            a = alphas[i] * exponents[i] if i <= jump else exponents[i]
+            factors[i].append((int(cycles[k + 1]), float(a)))
+        last = jump + 1
+    return factors
+
+
+def conv_same_length(n_samples, taps_list):
+    """Smallest power-of-two circular length that reproduces fftconvolve(x, taps, 'same') for every kernel."""
+    need = 16
+    for taps in taps_list:
+        M = len(taps)
+        c0 = (M - 1) // 2
+        need = max(need, n_samples + max(min(c0, n_samples - 1), min(M - 1 - c0, n_samples - 1)))
+    L = 16
+    while L < need:
+        L <<= 1
+    return L
+
+
+def conv_same_spectrum(taps, n_samples, L):
+    """FFT_L(h) / L with h[d mod L] = taps[d + (M-1)//2], |d| < n_samples (taps that cannot reach an output are dropped)."""
+    taps = np.asarray(taps, dtype=np.complex128)
+    M = len(taps)
+    c0 = (M - 1) // 2
+    d = np.arange(-min(c0, n_samples - 1), min(M - 1 - c0, n_samples - 1) + 1)
+    h = np.zeros(L, dtype=np.complex128)
+    h[d % L] = taps[d + c0]
+    return np.fft.fft(h) / L

@@ -145,6 +145,41 @@ int spyb_gather_rows(const float* src, int n_trials, long long src_trial_stride,
 /* x *= s on n float32 (trial mean `/= nTrials`, computational_routine.py:1030-1032) */
 int spyb_scale(float* x, long long n, float s, void* stream);
 
+/*
+ * Granger causality path (float64 / complex128 like the reference, AV_compRoutines.py:395).  These three calls
+ * synchronise `stream` internally: the regularisation ladder and Wilson's iteration are data dependent.
+ * `work` is caller-owned device scratch of at least spyb_*_workspace_bytes().  `_host` pointers are host memory.
+ *
+ * spyb_regularize_csd replaces syncopy/connectivity/wilson_sf.py:197-254 (`regularize_csd`):
+ *   csd       [n_freq][n_chan][n_chan] complex64 (trial-averaged cross spectra)
+ *   out       [n_freq][n_chan][n_chan] complex128 = csd + eps*I (eps = 0 when no regularisation was needed)
+ *   eps_host  0 (not needed), the factor used, or -1 (cond_max not reached even with eps_max; out then holds the
+ *             last attempt, csd + eps_max*I)
+ *   cond0_host  largest 2-norm condition number over the frequencies of the input
+ *   The condition numbers come from the extreme |eigenvalues| of the Hermitian matrices (Householder
+ *   tridiagonalisation + Sturm bisection in float64) instead of LAPACK's SVD.
+ *
+ * spyb_wilson replaces syncopy/connectivity/wilson_sf.py:16-194 (`wilson_sf`, direct_inversion=True):
+ *   csd       [n_freq][n_chan][n_chan] complex128, one-sided spectrum (the mirror to negative frequencies of
+ *             wilson_sf.py:63 is implicit), positive definite; n_chan <= 256
+ *   H         [n_freq][n_chan][n_chan] complex128 transfer function, Sigma [n_chan][n_chan] float64 noise covariance
+ *   converged_host / err_host / iters_host   convergence flag, final max relative error, iterations done
+ *   Returns non-zero (message: "not positive definite" / "singular") where NumPy would raise LinAlgError.
+ *
+ * spyb_granger replaces syncopy/connectivity/granger.py:10-79:
+ *   out [n_freq][n_chan][n_chan] float32, out[f][i][j] = Granger causality i -> j.
+ */
+long long spyb_regularize_workspace_bytes(int n_freq, int n_chan);
+int spyb_regularize_csd(const void* csd, int n_freq, int n_chan, double cond_max, double eps_max, int n_steps,
+                        void* out, double* eps_host, double* cond0_host, void* work, long long work_bytes,
+                        void* stream);
+long long spyb_wilson_workspace_bytes(int n_freq, int n_chan);
+int spyb_wilson(const void* csd, int n_freq, int n_chan, int n_iter, double rtol, void* H, double* Sigma,
+                int* converged_host, double* err_host, int* iters_host, void* work, long long work_bytes,
+                void* stream);
+int spyb_granger(const void* csd, const void* H, const double* Sigma, int n_freq, int n_chan, float* out,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

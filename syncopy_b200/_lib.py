@@ -18,7 +18,8 @@ class SpybError(RuntimeError):
 
 _lib = None
 
-_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+_vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+_dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
 
 # name -> (restype, argtypes); must list every symbol of include/spyb200.h
 PROTOTYPES = {
@@ -39,6 +40,11 @@ PROTOTYPES = {
     "spyb_cwt": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "spyb_gather_rows": (_i, [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp]),
     "spyb_scale": (_i, [_vp, _ll, _f, _vp]),
+    "spyb_regularize_workspace_bytes": (_ll, [_i, _i]),
+    "spyb_regularize_csd": (_i, [_vp, _i, _i, _d, _d, _i, _vp, _dp, _dp, _vp, _ll, _vp]),
+    "spyb_wilson_workspace_bytes": (_ll, [_i, _i]),
+    "spyb_wilson": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _ip, _dp, _ip, _vp, _ll, _vp]),
+    "spyb_granger": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
 }
 
 

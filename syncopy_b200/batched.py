@@ -215,6 +215,31 @@ def coherence(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper
     return _finish(coh, to_host, out_host), res.freqs
 
 
+def granger(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_opt=None, polyremoval=0,
+            rtol=5e-6, nIter=100, cond_max=1e4, to_host=False, engine=None, impl=0, reduce_group=None):
+    """
+    `connectivityanalysis(method='granger')` compute chain: CrossSpectra(keeptrials=False, demean_taper=True)
+    followed by GrangerCausality (syncopy/connectivity/connectivity_analysis.py:576,864; AV_compRoutines.py:292-412).
+    With `reduce_group`, `trials` is this rank's shard: the CSD sum is all-reduced and every rank then runs the
+    (replicated) factorisation.  Returns (granger [1, nFreq, C, C] float32, metadata dict, freqs).
+    """
+    eng = engine or get_engine()
+    res = cross_spectra_sum(trials, samplerate, nSamples, foi, taper, taper_opt, True, polyremoval,
+                            engine=eng, impl=impl)
+    n_total = res.n_trials
+    if reduce_group is not None:
+        from .distributed import allreduce_csd
+        n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group)
+    csd_av = eng.scale_(res.csd_sum, 1.0 / n_total)
+    reg, factor, ini_cn = eng.regularize_csd(csd_av, cond_max=cond_max, eps_max=1e-1)
+    H, Sigma, conv, err, iters = eng.wilson_sf(reg, n_iter=nIter, rtol=rtol)
+    G = eng.granger(reg, H, Sigma)[None]
+    meta = {"converged--bool": np.array(conv), "max rel. err--float": np.array(err),
+            "reg. factor--float": np.array(factor), "initial cond. num--float": np.array(np.float32(ini_cn)),
+            "iterations": iters}
+    return (G.cpu().numpy() if to_host else G), meta, res.freqs
+
+
 def _conv_transform(eng, trials, plan_key, make_taps, polyremoval, output, to_host, trial_chunk):
     x = _device_trials(eng, trials)
     B, n_sig, n_chan = x.shape

@@ -8,6 +8,7 @@ the arithmetic executed by libspyb200 on the GPU.
     cross_spectra_cF            <- syncopy/connectivity/ST_compRoutines.py:268-424
     spectral_dyadic_product_cF  <- syncopy/connectivity/ST_compRoutines.py:29-117
     normalize_csd_cF            <- syncopy/connectivity/AV_compRoutines.py:35-112
+    granger_cF                  <- syncopy/connectivity/AV_compRoutines.py:292-412
     wavelet_cF                  <- syncopy/specest/compRoutines.py:482-595
     superlet_cF                 <- syncopy/specest/compRoutines.py:654-762
 
@@ -214,6 +215,28 @@ def normalize_csd_cF(csd_av_dat, output="abs", chunkShape=None, noCompute=False)
 # ---------------------------------------------------------------------------
 # freqanalysis: wavelet / superlet
 # ---------------------------------------------------------------------------
+
+def granger_cF(csd_av_dat, rtol=5e-6, nIter=100, cond_max=1e4, chunkShape=None, noCompute=False):
+    """
+    Regularisation ladder -> Wilson factorisation -> Geweke-Granger causality of the trial-averaged cross
+    spectra `csd_av_dat` [1, nFreq, C, C] (AV_compRoutines.py:378-412).  Returns float32 [1, nFreq, C, C] and the
+    reference's metadata dict.
+    """
+    if noCompute:
+        return csd_av_dat.shape, hm.spectralDTypes["abs"]
+    eng = get_engine()
+    csd = eng.to_device(np.ascontiguousarray(csd_av_dat[0], dtype=np.complex64), dtype=torch.complex64)
+    reg, factor, ini_cn = eng.regularize_csd(csd, cond_max=cond_max, eps_max=1e-1)
+    H, Sigma, conv, err, _ = eng.wilson_sf(reg, n_iter=nIter, rtol=rtol)
+    G = eng.granger(reg, H, Sigma)
+    meta = {
+        "converged--bool": np.array(conv),
+        "max rel. err--float": np.array(err),
+        "reg. factor--float": np.array(factor),
+        "initial cond. num--float": np.array(np.float32(ini_cn)),
+    }
+    return G[None].cpu().numpy(), meta
+
 
 def _plan_key(obj):
     """Hashable identity of a wavelet object (class name + public attributes)."""

@@ -139,4 +139,31 @@ int spyb_scale(float* x, long long n, float s, void* stream) {
     return scale_inplace(x, n, s, static_cast<cudaStream_t>(stream));
 }
 
+long long spyb_regularize_workspace_bytes(int n_freq, int n_chan) {
+    return regularize_workspace_bytes(n_freq, n_chan);
+}
+
+int spyb_regularize_csd(const void* csd, int n_freq, int n_chan, double cond_max, double eps_max, int n_steps,
+                        void* out, double* eps_host, double* cond0_host, void* work, long long work_bytes,
+                        void* stream) {
+    if (!eps_host || !cond0_host) return fail("eps_host / cond0_host must not be NULL");
+    return regularize_csd(csd, n_freq, n_chan, cond_max, eps_max, n_steps, out, eps_host, cond0_host, work,
+                          work_bytes, static_cast<cudaStream_t>(stream));
+}
+
+long long spyb_wilson_workspace_bytes(int n_freq, int n_chan) { return wilson_workspace_bytes(n_freq, n_chan); }
+
+int spyb_wilson(const void* csd, int n_freq, int n_chan, int n_iter, double rtol, void* H, double* Sigma,
+                int* converged_host, double* err_host, int* iters_host, void* work, long long work_bytes,
+                void* stream) {
+    if (!converged_host || !err_host) return fail("converged_host / err_host must not be NULL");
+    return wilson_sf(csd, n_freq, n_chan, n_iter, rtol, H, Sigma, converged_host, err_host, iters_host, work,
+                     work_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_granger(const void* csd, const void* H, const double* Sigma, int n_freq, int n_chan, float* out,
+                 void* stream) {
+    return granger(csd, H, Sigma, n_freq, n_chan, out, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

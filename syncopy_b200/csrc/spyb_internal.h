@@ -71,4 +71,16 @@ int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale,
                   cudaStream_t stream);
 int scale_inplace(float* x, long long n, float s, cudaStream_t stream);
 
+// Granger path: regularisation, Wilson spectral factorisation, Geweke-Granger formula (wilson.cu); FP64
+long long regularize_workspace_bytes(int n_freq, int n_chan);
+int regularize_csd(const void* csd_c64, int n_freq, int n_chan, double cond_max, double eps_max, int n_steps,
+                   void* out_c128, double* eps_host, double* cond0_host, void* work, long long work_bytes,
+                   cudaStream_t stream);
+long long wilson_workspace_bytes(int n_freq, int n_chan);
+int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double rtol, void* H_out, double* Sigma_out,
+              int* converged_host, double* err_host, int* iters_host, void* work, long long work_bytes,
+              cudaStream_t stream);
+int granger(const void* csd_c128, const void* H, const double* Sigma, int n_freq, int n_chan, float* out,
+            cudaStream_t stream);
+
 }  // namespace spyb

@@ -263,6 +263,64 @@ class Engine:
                                              out.data_ptr(), self.stream()))
         return out
 
+    # ------------------------------------------------------------------ K7-K9: Granger causality (float64)
+    def _workspace(self, nbytes):
+        """Grow-only device scratch shared by the Granger kernels."""
+        ws = self._tables.get("workspace")
+        if ws is None or ws.numel() < nbytes:
+            self._tables["workspace"] = None
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.tdev)
+            self._tables["workspace"] = ws
+        return ws
+
+    def regularize_csd(self, csd, cond_max=1e3, eps_max=1e-3, n_steps=15):
+        """
+        csd [nF, C, C] complex64 CUDA -> (csd + eps*I as complex128, factor, initial condition number);
+        factor is 0 / eps / -1 exactly as `regularize_csd` reports it (wilson_sf.py:243-254).
+        """
+        import ctypes as C
+        assert csd.is_cuda and csd.dtype == torch.complex64 and csd.dim() == 3 and csd.is_contiguous()
+        nF, Cn, _ = csd.shape
+        out = torch.empty((nF, Cn, Cn), dtype=torch.complex128, device=self.tdev)
+        nbytes = self.lib.spyb_regularize_workspace_bytes(nF, Cn)
+        ws = self._workspace(nbytes)
+        eps, cond0 = C.c_double(0.0), C.c_double(0.0)
+        _lib.check(self.lib.spyb_regularize_csd(csd.data_ptr(), nF, Cn, float(cond_max), float(eps_max),
+                                                int(n_steps), out.data_ptr(), C.byref(eps), C.byref(cond0),
+                                                ws.data_ptr(), ws.numel(), self.stream()))
+        factor = eps.value
+        if factor == 0.0 or factor == -1.0:
+            factor = int(factor)
+        return out, factor, cond0.value
+
+    def wilson_sf(self, csd, n_iter=100, rtol=1e-6):
+        """
+        csd [nF, C, C] complex128 CUDA (one-sided) -> (H [nF, C, C] complex128, Sigma [C, C] float64,
+        converged, err, iterations)  -- wilson_sf.py:16-120.
+        """
+        import ctypes as C
+        assert csd.is_cuda and csd.dtype == torch.complex128 and csd.dim() == 3 and csd.is_contiguous()
+        nF, Cn, _ = csd.shape
+        H = torch.empty((nF, Cn, Cn), dtype=torch.complex128, device=self.tdev)
+        Sigma = torch.empty((Cn, Cn), dtype=torch.float64, device=self.tdev)
+        nbytes = self.lib.spyb_wilson_workspace_bytes(nF, Cn)
+        ws = self._workspace(nbytes)
+        conv, iters, err = C.c_int(0), C.c_int(0), C.c_double(0.0)
+        _lib.check(self.lib.spyb_wilson(csd.data_ptr(), nF, Cn, int(n_iter), float(rtol), H.data_ptr(),
+                                        Sigma.data_ptr(), C.byref(conv), C.byref(err), C.byref(iters),
+                                        ws.data_ptr(), ws.numel(), self.stream()))
+        return H, Sigma, bool(conv.value), err.value, iters.value
+
+    def granger(self, csd, H, Sigma):
+        """granger.py:10-79 on CUDA tensors -> [nF, C, C] float32."""
+        assert csd.dtype == torch.complex128 and H.dtype == torch.complex128 and Sigma.dtype == torch.float64
+        assert csd.is_contiguous() and H.is_contiguous() and Sigma.is_contiguous()
+        nF, Cn, _ = csd.shape
+        out = torch.empty((nF, Cn, Cn), dtype=torch.float32, device=self.tdev)
+        _lib.check(self.lib.spyb_granger(csd.data_ptr(), H.data_ptr(), Sigma.data_ptr(), nF, Cn, out.data_ptr(),
+                                         self.stream()))
+        return out
+
     def scale_(self, t, s):
         """In-place t *= s for float32 / complex64 CUDA tensors."""
         assert t.is_cuda and t.is_contiguous()

@@ -19,34 +19,14 @@
 // FFT: a[i] = z[i] conj(b[i]), Z[k] = conj(b[k]) * IFFT(FFT(a) * FFT(b))[k], b[i] = e^{i pi i^2/n}.
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "mtm_args.cuh"
 #include "plan.cuh"
 #include "spyb_internal.h"
 
+#include <cstdlib>
+
 namespace spyb {
 
-struct MtmArgs {
-    const float* x;            // [trial][sample][channel]
-    long long trial_stride;    // elements between trials
-    int n_trials, n_samples, n_chan;
-    int n_win;                 // detrend + taper window length (samples taken from the signal)
-    int n_dft;                 // logical DFT length (>= n_win)
-    int frame_start0, hop, n_frames;   // frame f starts at sample frame_start0 + f*hop (may be < 0: zeros)
-    const float* tapers;       // [n_tapers][n_win]
-    int n_tapers;
-    int polyremoval;           // -1 none, 0 de-mean, 1 linear (over the n_win window, zeros included)
-    int demean_taper;          // subtract the mean of the tapered window (mtmfft.py:114-116)
-    float scale;               // spectrum scale (sqrt(2)/norm), the 1/2 of the pair split is folded in by the kernel
-    const int* freq_idx;       // optional gather list (bins of the one-sided spectrum), may be null
-    int n_freq_out;
-    int out_kind, keeptapers;
-    void* out;                 // float or float2 elements
-    long long so_trial, so_frame, so_taper, so_freq;   // output strides in elements; channel stride is 1
-    int vec_in, vec_out;       // alignment allows 8-byte input loads / paired output stores
-    float* chan_amax;          // optional [n_chan]: running max(|re|,|im|) of the scaled spectrum
-    const float2* tw;
-    const float2* chirp;
-    const float2* bhat;
-};
 
 // Sum `NV` values over the NT threads that share (g, p).  red: [nwarps][P][NV] floats.
 template <int NT, int P, int NV>
@@ -300,7 +280,9 @@ static int launch_one(const MtmArgs& a, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N, NT = N / 16, GT = NT * P;
     constexpr int G = GT >= 256 ? 1 : 256 / GT;
     constexpr int THREADS = GT * G;
-    constexpr int MINB = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 4);
+    // 16 complex values per thread stay in registers across the passes: leave room for ~100 registers per thread
+    // wherever the thread count allows it (a 64-register cap spills them to local memory)
+    constexpr int MINB = THREADS >= 512 ? 1 : 512 / THREADS;
     auto kern = mtm_kernel<LOG2N, P, BLUE, THREADS, MINB>;
     const size_t smem = (size_t)G * fft_padded_len(N) * P * sizeof(float2) +
                         (size_t)(THREADS / 32 + 1) * P * 4 * sizeof(float);
@@ -331,7 +313,12 @@ static int launch_log2(int log2n, const MtmArgs& a, cudaStream_t st) {
         case 9:  return launch_one<9, 4, BLUE>(a, st);
         case 10: return launch_one<10, 4, BLUE>(a, st);
         case 11: return launch_one<11, 4, BLUE>(a, st);
-        case 12: return launch_one<12, 4, BLUE>(a, st);
+        case 12: {
+            static const int p12 = getenv("SPYB_MTM_P12") ? atoi(getenv("SPYB_MTM_P12")) : 4;
+            if (p12 == 1) return launch_one<12, 1, BLUE>(a, st);
+            if (p12 == 2) return launch_one<12, 2, BLUE>(a, st);
+            return launch_one<12, 4, BLUE>(a, st);
+        }
         case 13: return launch_one<13, 2, BLUE>(a, st);
         case 14: return launch_one<14, 1, BLUE>(a, st);
         default: return fail("unsupported block FFT size 2^%d", log2n);
@@ -368,7 +355,16 @@ int mtm_frames(const MtmFramesDesc& d, cudaStream_t stream) {
     const bool even_out = (d.so_trial % 2 == 0) && (d.so_frame % 2 == 0) && (d.so_taper % 2 == 0) &&
                           (d.so_freq % 2 == 0) && (reinterpret_cast<uintptr_t>(d.out) % (2 * elem) == 0);
     a.vec_out = even_out ? 1 : 0;
+    a.vec16 = ((d.n_chan % 4 == 0) && (d.trial_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(d.x) % 16 == 0)) ? 1 : 0;
+    a.tw_dif = pl->tw_dif;
 
+    // power-of-two lengths >= 256 run on the shared-memory-resident in-place kernel (mtm_dif.cu); short
+    // windows (several frames per block) and Bluestein lengths on the Stockham kernel below
+    static const bool force_stockham = getenv("SPYB_MTM_STOCKHAM") != nullptr;
+    if (!pl->bluestein && !force_stockham) {
+        const int rc = mtm_launch_dif(pl->log2n, a, stream);
+        if (rc >= 0) return rc;
+    }
     return pl->bluestein ? launch_log2<true>(pl->log2n, a, stream) : launch_log2<false>(pl->log2n, a, stream);
 }
 

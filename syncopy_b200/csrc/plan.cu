@@ -79,6 +79,28 @@ std::vector<float2> make_pass_twiddles(int log2n) {
     if (rlast > 1) emit(rlast);
     return tw;
 }
+
+// twiddles of the in-place decimation-in-frequency passes (mtm_dif.cu), in execution order: the pass of radix R at
+// butterfly distance `stride` multiplies output q of the butterfly at offset o by W_{R*stride}^{o*q}, stored at
+// [(q-1)*stride + o]; the last pass (stride 1) needs none.
+std::vector<float2> make_dif_twiddles(int log2n) {
+    std::vector<float2> tw;
+    const int q16 = log2n / 4;
+    long long stride = 1LL << log2n;
+    for (int i = 0; i < q16; ++i) {
+        stride /= 16;
+        if (stride > 1) {
+            const long long den = 16 * stride;
+            for (int q = 1; q < 16; ++q)
+                for (long long o = 0; o < stride; ++o) {
+                    const long long num = (o * q) % den;
+                    const double ang = -2.0 * kPi * double(num) / double(den);
+                    tw.push_back(make_float2(float(std::cos(ang)), float(std::sin(ang))));
+                }
+        }
+    }
+    return tw;
+}
 }  // namespace
 
 const FftPlan* get_fft_plan(int n_dft) {
@@ -106,6 +128,9 @@ const FftPlan* get_fft_plan(int n_dft) {
         return nullptr;
     }
     if (!upload(make_pass_twiddles(pl->log2n), &pl->tw)) { fail("plan upload failed"); delete pl; return nullptr; }
+    if (!pl->bluestein && !upload(make_dif_twiddles(pl->log2n), &pl->tw_dif)) {
+        fail("plan upload failed"); delete pl; return nullptr;
+    }
 
     if (pl->bluestein) {
         const int n = n_dft, M = 1 << pl->log2n;

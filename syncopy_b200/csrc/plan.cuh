@@ -10,7 +10,8 @@ struct FftPlan {
     int n_dft = 0;        // logical DFT length (any n >= 1)
     int log2n = 0;        // block FFT length N = 2^log2n (== n_dft when direct)
     bool bluestein = false;
-    const float2* tw = nullptr;      // pass twiddles for length N
+    const float2* tw = nullptr;      // pass twiddles for length N (Stockham passes, mtm.cu / cwt.cu)
+    const float2* tw_dif = nullptr;  // pass twiddles of the in-place DIF passes (mtm_dif.cu), direct lengths only
     const float2* chirp = nullptr;   // bluestein: b[i] = exp(+i pi i^2 / n), i < n
     const float2* bhat = nullptr;    // bluestein: FFT_N(b wrapped) / N   (the 1/N of the inverse folded in)
 };

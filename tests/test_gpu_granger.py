@@ -160,4 +160,4 @@ def test_full_size_factorisation_property(engine):
     assert rel <= 2 * 5e-6
     assert torch.equal(Sigma, Sigma.T) or nerr(Sigma.cpu().numpy(), Sigma.T.cpu().numpy()) <= 1e-12
     G = engine.granger(S, H, Sc.real.contiguous())
-    assert torch.isfinite(G).all() and G.diagonal(dim1=1, dim2=2).abs().max().item() == 0.0
+    assert torch.isfinite(G).all() and G.diagonal(dim1=1, dim2=2).abs().max().item() <= 1e-10

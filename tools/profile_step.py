@@ -27,13 +27,21 @@ opt = {"NW": 4.0, "Kmax": 7} if args.taper == "dpss" else None
 tapers = eng.taper_table(args.taper, N, N, opt)
 K = tapers.shape[0]
 nF = N // 2 + 1
-spectra = torch.empty((nF, T * K, C), dtype=torch.complex64, device=eng.tdev)
+use_tc = args.csd_impl != 1 and eng.csd_planar_supported(C)
+if use_tc:
+    spectra = torch.empty((nF, T * K, 2, C), dtype=torch.float32, device=eng.tdev)
+else:
+    spectra = torch.empty((nF, T * K, C), dtype=torch.complex64, device=eng.tdev)
 csd = torch.empty((nF, C, C), dtype=torch.complex64, device=eng.tdev)
 coh = torch.empty((1, nF, C, C), dtype=torch.float32, device=eng.tdev)
 for _ in range(args.iters):
-    eng.mtmfft(x, tapers, N, hm.mtmfft_scale(N, N), polyremoval=0, output="fourier", out=spectra, freq_major=True)
+    eng.mtmfft(x, tapers, N, hm.mtmfft_scale(N, N), polyremoval=0, output="fourier_planar" if use_tc else "fourier",
+               out=spectra, freq_major=True)
     if not args.skip_csd:
-        eng.csd_accumulate(spectra, acc=csd, alpha=1.0 / K, impl=args.csd_impl)
+        if use_tc:
+            eng.csd_accumulate_planar(spectra, acc=csd, alpha=1.0 / K)
+        else:
+            eng.csd_accumulate(spectra, acc=csd, alpha=1.0 / K, impl=1)
         eng.csd_normalize(csd[None], output="abs", pre_scale=1.0 / T, out=coh)
 torch.cuda.synchronize()
 print("done", float(coh.sum()) if not args.skip_csd else 0.0)

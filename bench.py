@@ -60,19 +60,41 @@ def config_dict(args, n_gpus):
 # CPU arm: the reference algorithm (oracle port) on host cores
 # ----------------------------------------------------------------------------------------------
 
-def _cpu_one_trial(job):
+_SHARED = {}
+
+
+def _cpu_worker(job):
+    """One pool worker: its share of the sample's trials, accumulated locally like the reference's
+    sequential `+=` (computational_routine.py:1025), partial sum left in shared memory."""
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    seed, taper, taper_opt = job
+    wid, seeds, taper, taper_opt = job
     from oracle import connectivity as oc
     from oracle import synth
-    x = synth.white_noise_trial(N_SAMPLES, N_CHAN, seed)
-    cs, _ = oc.cross_spectra_cF(x, FS, taper=taper, taper_opt=taper_opt, polyremoval=0)
-    return cs
+    part = _SHARED["partials"][wid]
+    for k, seed in enumerate(seeds):
+        x = synth.white_noise_trial(N_SAMPLES, N_CHAN, int(seed))
+        cs, _ = oc.cross_spectra_cF(x, FS, taper=taper, taper_opt=taper_opt, polyremoval=0)
+        if k == 0:
+            part[...] = cs[0]
+        else:
+            part += cs[0]
+    return wid
+
+
+_FIXED_COST = {}
 
 
 def cpu_reference_sample(taper, n_workers=None, trials_per_worker=1):
-    """One task per trial over a process pool (the reference's Dask LocalCluster semantics,
-    computational_routine.py:926-930), trial sum + mean + normalisation in the parent."""
+    """
+    The reference algorithm (oracle port) on the host cores, on a bounded sample of the workload:
+    one process per worker, one task per trial like the reference's Dask path
+    (computational_routine.py:926-930), every worker summing its trials in place, then the parent adds the
+    partial sums, divides by the trial count and runs normalize_csd once (connectivity_analysis.py:677-679).
+    The per-trial cost measured under full parallel load and the once-per-job cost (reduction + normalisation,
+    measured on the first call and reused) are combined into the throughput of the full 200-trial job:
+        value = 200 / (ceil(200 / workers) * t_trial + t_once).
+    """
+    import mmap
     from oracle import connectivity as oc
     from oracle import synth
     w = workload_cfg(taper)
@@ -82,25 +104,43 @@ def cpu_reference_sample(taper, n_workers=None, trials_per_worker=1):
         mem_gb = psutil.virtual_memory().available / 2 ** 30
     except Exception:
         mem_gb = 64
-    per_proc_gb = 4.5 + 1.1 * w["K"]          # [K, F, C, C] complex64 temporaries of the reference
+    per_proc_gb = 5.6 + 1.1 * w["K"]          # [K, F, C, C] complex64 temporaries + the partial sum
     if n_workers is None:
-        n_workers = int(max(1, min(cores, 32, mem_gb // per_proc_gb)))
+        n_workers = int(max(1, min(cores, 32, (mem_gb - 4) // per_proc_gb)))
+    n_freq = N_SAMPLES // 2 + 1
     n_trials = n_workers * trials_per_worker
     seeds = synth.trial_seeds(n_trials)
-    jobs = [(int(s), w["taper"], w["taper_opt"]) for s in seeds]
+    nbytes = n_workers * n_freq * N_CHAN * N_CHAN * 8
+    buf = mmap.mmap(-1, nbytes)                # anonymous shared mapping, inherited by the forked workers
+    _SHARED["partials"] = np.frombuffer(buf, dtype=np.complex64).reshape(n_workers, n_freq, N_CHAN, N_CHAN)
+    jobs = [(i, [int(sd) for sd in seeds[i::n_workers]], w["taper"], w["taper_opt"]) for i in range(n_workers)]
     ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
     with ctx.Pool(n_workers) as pool:
-        acc = None
-        for cs in pool.imap_unordered(_cpu_one_trial, jobs):
-            acc = cs.copy() if acc is None else acc.__iadd__(cs)
-    acc /= n_trials
-    coh = oc.normalize_csd(acc, "abs")
-    dt = time.perf_counter() - t0
-    assert np.isfinite(coh).all()
-    return dict(value=n_trials / dt, unit=UNIT, cores=n_workers, kind="port",
-                sample=f"{n_trials} trials of the workload ({trials_per_worker}/worker, one process per worker, "
-                       f"1 BLAS thread each; incl. trial mean + normalize_csd), {dt:.1f} s wall"), dt
+        t0 = time.perf_counter()
+        list(pool.imap_unordered(_cpu_worker, jobs))
+        t_pool = time.perf_counter() - t0
+    t_trial = t_pool / trials_per_worker
+    key = (taper, n_workers)
+    if key not in _FIXED_COST:
+        t0 = time.perf_counter()
+        acc = _SHARED["partials"][0].copy()
+        for i in range(1, n_workers):
+            acc += _SHARED["partials"][i]
+        acc /= n_trials
+        coh = oc.normalize_csd(acc, "abs")
+        _FIXED_COST[key] = time.perf_counter() - t0
+        assert np.isfinite(coh).all()
+        del acc, coh
+    t_once = _FIXED_COST[key]
+    _SHARED.clear()
+    del buf
+    rounds = -(-N_TRIALS // n_workers)
+    job_s = rounds * t_trial + t_once
+    return dict(value=N_TRIALS / job_s, unit=UNIT, cores=n_workers, kind="port",
+                sample=f"{n_trials} trials ({trials_per_worker}/worker, one process per worker, 1 BLAS thread "
+                       f"each): {t_trial:.2f} s per trial and worker under load; partial-sum reduction + trial mean "
+                       f"+ normalize_csd once per job: {t_once:.1f} s; extrapolated to the {N_TRIALS}-trial job = "
+                       f"{rounds} rounds x {t_trial:.2f} s + {t_once:.1f} s = {job_s:.1f} s"), t_pool
 
 
 def run_reference_arm(args):
@@ -118,7 +158,7 @@ def run_reference_arm(args):
     info["value"] = value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * N_TRIALS / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT in f64, CSD in c64)",
         "data": "synthetic", "config": config_dict(args, args.gpus), "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -3,8 +3,8 @@
 // Same arithmetic as mtm.cu (detrend -> taper -> [de-mean] -> real FFT of two channels packed as one complex
 // series -> scale -> gather -> convert -> [taper mean]); different execution shape, chosen for HBM throughput:
 //
-//   * a block owns P channel pairs of one frame: N x 2P floats = N*P*8 bytes of shared memory, copied from HBM
-//     with 16-byte cp.async (no register staging), so for N = 4096 three 64 KB blocks share an SM and their
+//   * a block owns P channel pairs of one frame: N x 2P floats = N*P*8 bytes of shared memory, filled with 16-byte
+//     row copies (the detrending sums ride along), so for N = 4096 several 64 KB blocks share an SM and their
 //     load / FFT / store phases overlap;
 //   * radix-16 decimation-in-frequency passes work in place (gather 16 values, butterfly, twiddle, write back to
 //     the same 16 slots), so a thread can process several butterflies of a pass one after the other with only 16
@@ -42,38 +42,35 @@ __device__ __forceinline__ int dif_pos(int k) {
     return pos | k;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
 // One in-place DIF pass of radix R over butterflies at distance STRIDE.
+// swz() is linear over XOR and base has zero bits where r*STRIDE lives, so the slot of element r is
+// swz(base) ^ swz(r*STRIDE): one XOR with a compile-time constant per shared-memory access.
 template <int LOG2N, int P, int THREADS, int R, int STRIDE, bool FIRST, typename Pre>
 __device__ __forceinline__ void dif_pass(float2* __restrict__ s, const float2* __restrict__ tw, int tid, Pre& pre) {
     constexpr int N = 1 << LOG2N;
     constexpr int ITEMS = (N / R) * P;
+    char* sb = reinterpret_cast<char*>(s);
 #pragma unroll 1
     for (int item = tid; item < ITEMS; item += THREADS) {
-        const int p = item % P, u = item / P;
-        const int o = u % STRIDE, base = (u / STRIDE) * (R * STRIDE) + o;
+        const unsigned p = (unsigned)item % P, u = (unsigned)item / P;
+        const unsigned o = u % STRIDE, base = (u / STRIDE) * (R * STRIDE) + o;
+        const unsigned a0 = ((unsigned)swz((int)base) * P + p) * 8u;
         float2 x[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[r] = s[swz(base + r * STRIDE) * P + p];
-        if constexpr (FIRST) pre(x, base);
+        for (int r = 0; r < R; ++r) x[r] = *reinterpret_cast<const float2*>(sb + (a0 ^ (unsigned)(swz(r * STRIDE) * P * 8)));
+        if constexpr (FIRST) pre(x, (int)base);
         Radix<R>::run(x);
         if constexpr (STRIDE > 1) {
+            const float2* __restrict__ two = tw + o;
 #pragma unroll
             for (int q = 1; q < R; ++q) {
-                constexpr int dummy = 0; (void)dummy;
                 const int reg = Radix<R>::reg_of(q);
-                x[reg] = cmul(x[reg], __ldg(&tw[(q - 1) * STRIDE + o]));
+                x[reg] = cmul(x[reg], __ldg(two + (q - 1) * STRIDE));
             }
         }
 #pragma unroll
-        for (int q = 0; q < R; ++q) s[swz(base + q * STRIDE) * P + p] = x[Radix<R>::reg_of(q)];
+        for (int q = 0; q < R; ++q)
+            *reinterpret_cast<float2*>(sb + (a0 ^ (unsigned)(swz(q * STRIDE) * P * 8))) = x[Radix<R>::reg_of(q)];
     }
     __syncthreads();
 }
@@ -142,20 +139,41 @@ __global__ void __launch_bounds__(THREADS, MINB) mtm_dif_kernel(const MtmArgs a)
     const int n_win = a.n_win;
 
     // ---- raw tile -> shared memory (zeros outside the window / the trial) ----
-    auto load_tile = [&]() {
-        if (P >= 2 && a.vec16 && full_tile) {
-            constexpr int CH = P >= 2 ? P / 2 : 1;                 // 16-byte chunks per row
-#pragma unroll 4
-            for (int q = tid; q < N * CH; q += THREADS) {
-                const int n = q / CH, h = q % CH;
-                const long long m = start + n;
-                float2* dst = &s[swz(n) * P + 2 * h];
-                if (n < n_win && m >= 0 && m < a.n_samples)
-                    cp_async16(dst, xt + m * a.n_chan + c0 + 4 * h);
-                else
-                    *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    // 16-byte rows go through registers (LDG.128 -> STS.128: 4 shared-memory wavefronts per warp; cp.async scatters
+    // one wavefront per lane here because every lane's 16 bytes come from a different 1 KB-strided row), which
+    // also lets the detrending sums ride along with the first copy.
+    const float tmid = 0.5f * (float)(n_win - 1);
+    const bool vec_tile = P >= 2 && a.vec16 && full_tile;
+    constexpr int CH = P >= 2 ? P / 2 : 1;                          // 16-byte chunks per row
+    constexpr int RED_PER_WARP = CH * 8 > P * 4 ? CH * 8 : P * 4;
+    auto load_tile = [&](float (&sums)[8], const bool with_sums) {
+        if (vec_tile) {
+            const int h = tid % CH;
+            constexpr int ROWS_PER_STEP = THREADS / CH;
+            // every 16-byte load of the thread is issued before the first store: one HBM latency per tile
+            constexpr int UN = (N / ROWS_PER_STEP) < 16 ? (N / ROWS_PER_STEP) : 16;
+            const float* __restrict__ src = xt + c0 + 4 * h;
+            for (int n0 = tid / CH; n0 < N; n0 += UN * ROWS_PER_STEP) {
+                float4 v[UN];
+#pragma unroll
+                for (int i = 0; i < UN; ++i) {
+                    const int n = n0 + i * ROWS_PER_STEP;
+                    const long long m = start + n;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (n < n_win && m >= 0 && m < a.n_samples)
+                        v[i] = __ldg(reinterpret_cast<const float4*>(src + m * a.n_chan));
+                }
+#pragma unroll
+                for (int i = 0; i < UN; ++i) {
+                    const int n = n0 + i * ROWS_PER_STEP;
+                    if (n < N) *reinterpret_cast<float4*>(&s[swz(n) * P + 2 * h]) = v[i];
+                    if (with_sums && n < n_win) {
+                        const float t = (float)n - tmid;
+                        sums[0] += v[i].x; sums[1] += v[i].y; sums[2] += v[i].z; sums[3] += v[i].w;
+                        sums[4] += t * v[i].x; sums[5] += t * v[i].y; sums[6] += t * v[i].z; sums[7] += t * v[i].w;
+                    }
+                }
             }
-            cp_async_wait_all();
         } else {
 #pragma unroll 4
             for (int q = tid; q < N * P; q += THREADS) {
@@ -172,31 +190,46 @@ __global__ void __launch_bounds__(THREADS, MINB) mtm_dif_kernel(const MtmArgs a)
                     }
                 }
                 s[swz(n) * P + p] = val;
+                if (with_sums && n < n_win) {
+                    const float t = (float)n - tmid;
+                    sums[0] += val.x; sums[1] += val.y;
+                    sums[4] += t * val.x; sums[5] += t * val.y;
+                }
             }
         }
         __syncthreads();
     };
 
-    load_tile();
-
     // ---- detrending statistics over the window (scipy.signal.detrend, constant / linear) ----
     float mean_a = 0.f, mean_b = 0.f, slope_a = 0.f, slope_b = 0.f;
-    const float tmid = 0.5f * (float)(n_win - 1);
-    if (a.polyremoval >= 0) {
-        float sums[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int q = tid; q < n_win * P; q += THREADS) {
-            const int n = q / P;
-            const float2 v = s[swz(n) * P + p];
-            const float t = (float)n - tmid;
-            sums[0] += v.x; sums[1] += v.y;
-            sums[2] += t * v.x; sums[3] += t * v.y;
-        }
-        pair_reduce<P, THREADS, 4>(sums, red, tid);
-        const float inv_n = 1.f / (float)n_win;
-        mean_a = sums[0] * inv_n; mean_b = sums[1] * inv_n;
-        if (a.polyremoval == 1 && n_win > 1) {
-            const float stt = (float)((double)n_win * ((double)n_win * n_win - 1.0) / 12.0);
-            slope_a = sums[2] / stt; slope_b = sums[3] / stt;
+    {
+        float sums[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const bool want = a.polyremoval >= 0;
+        load_tile(sums, want);
+        if (want) {
+            float* stat = red + (THREADS / 32) * RED_PER_WARP;      // [2P channels][2]
+            if (vec_tile) {
+                // sums are per 16-byte chunk (4 channels); reduce over the threads that share the chunk
+                pair_reduce<CH, THREADS, 8>(sums, red, tid);
+                if (tid < CH) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { stat[(4 * tid + i) * 2] = sums[i]; stat[(4 * tid + i) * 2 + 1] = sums[4 + i]; }
+                }
+            } else {
+                float s4[4] = {sums[0], sums[1], sums[4], sums[5]};
+                pair_reduce<P, THREADS, 4>(s4, red, tid);
+                if (tid < P) {
+                    stat[(2 * tid) * 2] = s4[0]; stat[(2 * tid + 1) * 2] = s4[1];
+                    stat[(2 * tid) * 2 + 1] = s4[2]; stat[(2 * tid + 1) * 2 + 1] = s4[3];
+                }
+            }
+            __syncthreads();
+            const float inv_n = 1.f / (float)n_win;
+            mean_a = stat[(2 * p) * 2] * inv_n; mean_b = stat[(2 * p + 1) * 2] * inv_n;
+            if (a.polyremoval == 1 && n_win > 1) {
+                const float stt = (float)((double)n_win * ((double)n_win * n_win - 1.0) / 12.0);
+                slope_a = stat[(2 * p) * 2 + 1] / stt; slope_b = stat[(2 * p + 1) * 2 + 1] / stt;
+            }
         }
     }
 
@@ -205,7 +238,10 @@ __global__ void __launch_bounds__(THREADS, MINB) mtm_dif_kernel(const MtmArgs a)
     float amax_a = 0.f, amax_b = 0.f;
 
     for (int k = 0; k < a.n_tapers; ++k) {
-        if (k > 0) load_tile();                                     // the passes overwrote the raw samples
+        if (k > 0) {                                                // the passes overwrote the raw samples
+            float dummy[8];
+            load_tile(dummy, false);
+        }
         const float* __restrict__ win = a.tapers + (long long)k * n_win;
 
         // mean of the tapered window (mtmfft.py:114-116), subtracted inside the first pass
@@ -224,15 +260,26 @@ __global__ void __launch_bounds__(THREADS, MINB) mtm_dif_kernel(const MtmArgs a)
             tm_a = tsum[0] / (float)n_win; tm_b = tsum[1] / (float)n_win;
         }
 
+        const bool sloped = slope_a != 0.f || slope_b != 0.f;
         auto pre = [&](float2 (&x)[16], int base) {
+            const float* __restrict__ wb = win + base;
+            if (base + 15 * STRIDE0 < n_win && !sloped) {            // whole butterfly inside the window, no trend
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const int n = base + r * STRIDE0;
-                if (n < n_win) {
-                    const float t = (float)n - tmid;
-                    const float w = __ldg(win + n);
-                    x[r].x = (x[r].x - (mean_a + slope_a * t)) * w - tm_a;
-                    x[r].y = (x[r].y - (mean_b + slope_b * t)) * w - tm_b;
+                for (int r = 0; r < 16; ++r) {
+                    const float w = __ldg(wb + r * STRIDE0);
+                    x[r].x = (x[r].x - mean_a) * w - tm_a;
+                    x[r].y = (x[r].y - mean_b) * w - tm_b;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int n = base + r * STRIDE0;
+                    if (n < n_win) {
+                        const float t = (float)n - tmid;
+                        const float w = __ldg(wb + r * STRIDE0);
+                        x[r].x = (x[r].x - (mean_a + slope_a * t)) * w - tm_a;
+                        x[r].y = (x[r].y - (mean_b + slope_b * t)) * w - tm_b;
+                    }
                 }
             }
         };
@@ -323,7 +370,10 @@ template <int LOG2N, int P, int THREADS, int MINB>
 int launch_dif(const MtmArgs& a, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
     auto kern = mtm_dif_kernel<LOG2N, P, THREADS, MINB>;
-    const size_t smem = (size_t)N * P * sizeof(float2) + (size_t)(THREADS / 32) * P * 4 * sizeof(float) + 16;
+    constexpr int CH = P >= 2 ? P / 2 : 1;
+    constexpr int RED_PER_WARP = CH * 8 > P * 4 ? CH * 8 : P * 4;
+    const size_t smem = (size_t)N * P * sizeof(float2) + (size_t)(THREADS / 32) * RED_PER_WARP * sizeof(float) +
+                        (size_t)4 * P * sizeof(float) + 16;
     static bool configured = false;   // per template instantiation
     if (!configured) {
         SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -342,14 +392,21 @@ int launch_dif(const MtmArgs& a, cudaStream_t stream) {
 }  // namespace
 
 int mtm_launch_dif(int log2n, const MtmArgs& a, cudaStream_t st) {
-    // tuning knob for experiments: SPYB_MTM_DIF12 = 2 (default: 2 pairs, 3 blocks / SM) or 4 (4 pairs, 1 block / SM)
-    static const int p12 = getenv("SPYB_MTM_DIF12") ? atoi(getenv("SPYB_MTM_DIF12")) : 2;
+    // tuning knob for experiments (N = 4096): pairs / threads / blocks per SM
+    static const int p12 = getenv("SPYB_MTM_DIF12") ? atoi(getenv("SPYB_MTM_DIF12")) : 0;
     switch (log2n) {
         case 8:  return launch_dif<8, 4, 64, 12>(a, st);
         case 9:  return launch_dif<9, 4, 128, 6>(a, st);
         case 10: return launch_dif<10, 4, 256, 3>(a, st);
         case 11: return launch_dif<11, 4, 256, 3>(a, st);
-        case 12: return p12 == 4 ? launch_dif<12, 4, 512, 1>(a, st) : launch_dif<12, 2, 256, 3>(a, st);
+        case 12:
+            switch (p12) {
+                case 1: return launch_dif<12, 2, 256, 2>(a, st);
+                case 2: return launch_dif<12, 2, 128, 3>(a, st);
+                case 4: return launch_dif<12, 4, 256, 1>(a, st);
+                case 5: return launch_dif<12, 2, 256, 3>(a, st);
+                default: return launch_dif<12, 4, 512, 1>(a, st);
+            }
         case 13: return launch_dif<13, 2, 512, 1>(a, st);
         case 14: return launch_dif<14, 1, 512, 1>(a, st);
         default: return -1;

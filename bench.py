@@ -51,7 +51,11 @@ def config_dict(args, n_gpus):
                     f"{N_SAMPLES} smp fp32 per GPU, taper={w['taper']} (K={w['K']}), polyremoval=0, "
                     f"foi=None (2049 bins), output=abs, keeptrials=False",
         "trials_per_gpu": N_TRIALS, "n_channels": N_CHAN, "n_samples": N_SAMPLES, "n_tapers": w["K"],
-        "parallelism": f"trial-sharded x{n_gpus}" + (" + NCCL all-reduce of the CSD sum" if n_gpus > 1 else ""),
+        "parallelism": f"trial-sharded x{n_gpus}" + (
+            "; upper CSD tiles stored straight into the frequency-slab owner's slot buffer over NVLink P2P from the "
+            "tcgen05 epilogue, counter all-reduce as barrier, result left sharded by frequency slab"
+            if n_gpus > 1 and getattr(args, "csd_impl", 0) in (0, 2) else
+            (" + NCCL all-reduce of the CSD sum" if n_gpus > 1 else "")),
         "l2_policy": "inputs (839 MB/step) and spectra exceed the 126 MB L2; no explicit flush",
     }
 
@@ -268,31 +272,52 @@ def run_gpu_arm(args):
     n_freq = N_SAMPLES // 2 + 1
     tapers = eng.taper_table(w["taper"], N_SAMPLES, N_SAMPLES, w["taper_opt"])
     scale = hm.mtmfft_scale(N_SAMPLES, N_SAMPLES)
-    use_tc = args.csd_impl == 2 or (args.csd_impl == 0 and eng.csd_planar_supported(N_CHAN))
-    if use_tc:      # planar re|im rows: operand layout of the tcgen05 cross-spectral kernel
+    total_trials = N_TRIALS * world
+    group = dist.group.WORLD if world > 1 else None
+    # default path: tcgen05 contraction writing upper tiles into per-frequency-slab slot buffers (peer stores over
+    # NVLink for N > 1), then per-slab sum + normalisation; --csd-impl 1/3 select the older paths for comparison
+    mode = {0: "tiles", 2: "tiles", 1: "simt", 3: "planar"}[args.csd_impl]
+    if mode == "tiles" and not eng.csd_planar_supported(N_CHAN):
+        mode = "simt"
+    if mode == "tiles":
+        from syncopy_b200.distributed import get_tile_exchange
+        ex = get_tile_exchange(eng, n_freq, N_CHAN, group)
+        nf_local = ex.nf_local
+    else:
+        nf_local = n_freq
+    if mode in ("tiles", "planar"):   # planar re|im rows: operand layout of the tcgen05 cross-spectral kernel
         spectra = torch.empty((n_freq, N_TRIALS * K, 2, N_CHAN), dtype=torch.float32, device=dev)
     else:
         spectra = torch.empty((n_freq, N_TRIALS * K, N_CHAN), dtype=torch.complex64, device=dev)
-    csd_sum = torch.empty((n_freq, N_CHAN, N_CHAN), dtype=torch.complex64, device=dev)
-    coh = torch.empty((1, n_freq, N_CHAN, N_CHAN), dtype=torch.float32, device=dev)
+    csd_sum = None if mode == "tiles" else torch.empty((n_freq, N_CHAN, N_CHAN), dtype=torch.complex64, device=dev)
+    coh = torch.empty((1, nf_local, N_CHAN, N_CHAN), dtype=torch.float32, device=dev)
     coh_host = torch.empty(coh.shape, dtype=torch.float32).pin_memory()
-    total_trials = N_TRIALS * world
 
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
 
     def step(marks=None):
         if marks is not None:
             marks[0].record()
-        eng.mtmfft(x, tapers, N_SAMPLES, scale, polyremoval=0, output="fourier_planar" if use_tc else "fourier",
+        eng.mtmfft(x, tapers, N_SAMPLES, scale, polyremoval=0, output="fourier" if mode == "simt" else "fourier_planar",
                    keeptapers=True, out=spectra, freq_major=True)
         if marks is not None:
             marks[1].record()
-        if use_tc:
+        if mode == "tiles":
+            ex.accumulate(spectra, alpha=1.0 / K, beta=0.0)
+        elif mode == "planar":
             eng.csd_accumulate_planar(spectra, acc=csd_sum, alpha=1.0 / K, beta=0.0)
         else:
             eng.csd_accumulate(spectra, acc=csd_sum, alpha=1.0 / K, beta=0.0, impl=1)
         if marks is not None:
             marks[2].record()
+        if mode == "tiles":
+            ex.barrier(N_TRIALS, n_total=total_trials)       # counter all-reduce: every rank's tiles have landed
+            if marks is not None:
+                marks[3].record()
+            ex.normalize(total_trials, output="abs", out=coh[0])   # per-slab sum over ranks + normalisation
+            if marks is not None:
+                marks[4].record()
+            return
         if world > 1:
             dist.all_reduce(torch.view_as_real(csd_sum))
         if marks is not None:
@@ -335,8 +360,8 @@ def run_gpu_arm(args):
     # ---- end to end through the public API (pinned host in, pinned host out) ---------------------
     def e2e_step():
         c, _ = batched.coherence(host, FS, taper=w["taper"], taper_opt=w["taper_opt"], polyremoval=0,
-                                 output="abs", engine=eng, impl=args.csd_impl,
-                                 reduce_group=(dist.group.WORLD if world > 1 else None), out_host=coh_host)
+                                 output="abs", engine=eng, impl={0: 0, 2: 0, 1: 1, 3: 1}[args.csd_impl],
+                                 reduce_group=group, out_host=coh_host, gather=False)
         return c
 
     for _ in range(2):
@@ -373,21 +398,23 @@ def run_gpu_arm(args):
         tensor_peak = peaks["bf16_tflops_sustained"]
         achieved_tf = flops_alg / (csd_ms * 1e-3) / 1e12
         roofline = {
-            "kernel": "csd contraction (K2, %s)" % ("tcgen05 3xTF32" if use_tc else "CUDA-core FP32"), "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak,
+            "kernel": "csd contraction (K2, %s)" % ("CUDA-core FP32" if mode == "simt" else "tcgen05 3xTF32"), "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak,
             "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak, "traffic": None,
             "peak_source": f"{peaks['source']} bf16 dense sustained (kernel timed inside a long step)",
             "algorithmic": f"8*C^2*nFreq*K flop per trial = {flops_alg / N_TRIALS / 1e9:.3f} GFLOP, x{N_TRIALS} trials/launch",
             "share_of_step": float(csd_ms / ms_per_step),
         }
+        tile_frac = 0.75 if mode == "tiles" else 1.0                       # 3 of 4 128x128 tiles are stored
+        k3_bytes = csd_bytes * tile_frac * (world if mode == "tiles" else 1) * nf_local / n_freq + 4 * nf_local * N_CHAN * N_CHAN
         kernels = {
             "mtmfft (K1)": {"ms": float(fft_ms), "bound": "hbm",
                             "achieved_gbs": (in_bytes + spec_bytes) / (fft_ms * 1e-3) / 1e9,
                             "frac_of_hbm_peak": (in_bytes + spec_bytes) / (fft_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
             "csd (K2)": {"ms": float(csd_ms), "bound": "tensor", "achieved_tflops": achieved_tf,
-                         "bytes_gbs": (spec_bytes + csd_bytes) / (csd_ms * 1e-3) / 1e9},
-            "allreduce": {"ms": float(ar_ms)},
+                         "bytes_gbs": (spec_bytes + csd_bytes * tile_frac) / (csd_ms * 1e-3) / 1e9},
+            ("barrier" if mode == "tiles" else "allreduce"): {"ms": float(ar_ms)},
             "normalize (K3)": {"ms": float(norm_ms), "bound": "hbm",
-                               "achieved_gbs": (csd_bytes * 1.5) / (norm_ms * 1e-3) / 1e9},
+                               "achieved_gbs": k3_bytes / (norm_ms * 1e-3) / 1e9},
         }
         hbm_pipeline = {
             "algorithmic_bytes_per_trial": alg_bytes_per_trial,
@@ -422,7 +449,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--taper", default="hann", choices=["hann", "dpss"])
-    ap.add_argument("--csd-impl", dest="csd_impl", type=int, default=0, help="0 auto, 1 SIMT, 2 tcgen05")
+    ap.add_argument("--csd-impl", dest="csd_impl", type=int, default=0,
+                    help="0 tcgen05 + tile slots (default), 1 CUDA-core kernel + all-reduce, 3 tcgen05 full CSD + all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

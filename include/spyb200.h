@@ -106,6 +106,38 @@ int spyb_csd_accumulate_planar(const float* planes, long long sx_f, long long sx
                                int n_chan, float alpha, float beta, void* acc, void* stream);
 
 /*
+ * Sharded variant of the two calls above for the trial-averaged path (keeptrials=False,
+ * computational_routine.py:1022-1032 + csd.py:118-172) on one or several GPUs.  Frequencies are split into
+ * contiguous slabs, slab o = [f_begin_host[o], f_begin_host[o+1]) is owned by rank o.  spyb_csd_accumulate_tiles
+ * writes every upper-triangular 128x128 tile of frequency f (tile order (0,0), (0,1), (1,1); one tile for 128
+ * channels), scaled by alpha and unmirrored, into the owner's slot buffer
+ *     owner_base_host[o] + ((src_rank * nF_o + (f - f_begin[o])) * n_tiles + tile) * 128*128   (complex64)
+ * with plain stores -- owner_base_host[o] may be a peer-mapped pointer (CUDA IPC / NVLink P2P), so the transfer
+ * of a finished tile overlaps the tensor-core work on the next one and no collective moves the data.  After a
+ * barrier between the ranks, spyb_csd_normalize_tiles sums the n_src source slots of the local slab
+ * (slots [n_src][nF_local][n_tiles][128][128]), multiplies by pre_scale (1/nTrials), normalises and writes
+ * out [nF_local][n_chan][n_chan] (float32, or complex64 for out_kind 2) including the mirrored half.
+ * With one rank (n_owners = n_src = 1) the pair replaces spyb_csd_accumulate_planar + spyb_csd_normalize without
+ * ever materialising the mirrored CSD.  Eligibility as spyb_csd_planar_supported.
+ */
+int spyb_csd_tile_count(int n_chan);
+int spyb_csd_accumulate_tiles(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                              int n_chan, float alpha, float beta, void* const* owner_base_host,
+                              const int* f_begin_host, int n_owners, int src_rank, void* stream);
+int spyb_csd_normalize_tiles(const void* slots, int n_src, int n_freq_local, int n_chan, float pre_scale,
+                             int out_kind, void* out, void* stream);
+
+/*
+ * Slot buffers that other ranks of the node can write into (one process per GPU): plain cudaMalloc memory plus
+ * its 64-byte CUDA IPC handle; a peer rank maps it with spyb_peer_open (which also enables P2P access between
+ * its device and the owner's, NVLink on an NVSwitch node) and passes the mapped pointer as owner_base_host[o].
+ */
+int spyb_peer_alloc(long long bytes, void** ptr_out, unsigned char* handle64_out);
+int spyb_peer_open(const unsigned char* handle64, void** ptr_out);
+int spyb_peer_close(void* mapped_ptr);
+int spyb_peer_free(void* ptr);
+
+/*
  * Coherency + output conversion:  out = conv( pre*C_ij / sqrt(pre*C_ii * pre*C_jj) ).
  * Replaces: syncopy/connectivity/csd.py:118-172 (`normalize_csd`).
  *   csd [n_mat][n_chan][n_chan] complex64; out float32 or complex64 of the same shape.

@@ -9,6 +9,8 @@ Inputs are `[nTrials, nSamples, nChannels]` float32, either host `ndarray`s
 (copied through pinned memory) or CUDA tensors.  Outputs are CUDA tensors
 unless `to_host=True`.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -193,7 +195,7 @@ def _finish(result, to_host, out_host):
 
 def coherence(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_opt=None,
               polyremoval=0, output="abs", to_host=False, engine=None, impl=0, reduce_group=None,
-              out_host=None):
+              out_host=None, gather=True):
     """
     `connectivityanalysis(method='coh')` compute chain: CrossSpectra(keeptrials=False) followed by
     NormalizeCrossSpectra (syncopy/connectivity/connectivity_analysis.py:460-473,549,587-599,677-679).
@@ -202,9 +204,15 @@ def coherence(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper
     With `reduce_group` (a torch.distributed process group) `trials` is this rank's shard of the
     trial list: the trial-summed CSD and the trial count are all-reduced (the one collective of the
     path, replacing the reference's lock-serialised HDF5 `+=`, kwarg_decorators.py:722-735) and every
-    rank returns the full result.  Returns (coh [1, nFreq, C, C], freqs).
+    rank returns the full result.  Returns (coh [1, nFreq, C, C], freqs).  With `gather=False` a rank keeps only
+    the frequency slab it owns (coh [1, nFreq_slab, C, C] and that slab's frequencies) -- the layout in which each
+    rank would write its part of the result file.
     """
     eng = engine or get_engine()
+    n_chan = trials.shape[2]
+    if impl in (0, 2) and eng.csd_planar_supported(n_chan) and not os.environ.get("SPYB_NO_TILES"):
+        return _coherence_tiles(eng, trials, samplerate, nSamples, foi, taper, taper_opt, polyremoval, output,
+                                to_host, reduce_group, out_host, gather)
     res = cross_spectra_sum(trials, samplerate, nSamples, foi, taper, taper_opt, False, polyremoval,
                             engine=eng, impl=impl)
     n_total = res.n_trials
@@ -213,6 +221,52 @@ def coherence(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper
         n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group)
     coh = eng.csd_normalize(res.csd_sum[None], output=output, pre_scale=1.0 / n_total)
     return _finish(coh, to_host, out_host), res.freqs
+
+
+def _coherence_tiles(eng, trials, samplerate, nSamples, foi, taper, taper_opt, polyremoval, output, to_host,
+                     reduce_group, out_host, gather):
+    """
+    128 / 256 channels: tapered FFT -> tcgen05 contraction that writes only the upper 128x128 tiles, each
+    frequency straight into the slot buffer of the rank owning it (peer stores over NVLink for several ranks, see
+    distributed.TileExchange) -> per-slab sum over ranks + normalisation.  The mirrored CSD is never materialised.
+    """
+    import torch.distributed as dist
+    from .distributed import get_tile_exchange
+    x = _device_trials(eng, trials)
+    B, n_sig, n_chan = x.shape
+    nfft = n_sig if nSamples is None else int(nSamples)
+    freqs, fidx = _freq_selection(nfft, samplerate, foi)
+    n_freq = freqs.size
+    tapers = eng.taper_table(taper, n_sig, nfft, taper_opt)
+    K = tapers.shape[0]
+    scale = hm.mtmfft_scale(n_sig, nfft)
+    pr = hm.polyremoval_code(polyremoval)
+    ex = get_tile_exchange(eng, n_freq, n_chan, reduce_group)
+    chunk = max(1, min(B, MAX_SPECTRA_BYTES // max(1, n_freq * K * n_chan * 8)))
+    spectra = eng.scratch("planar_spectra", (n_freq, min(chunk, B) * K, 2, n_chan), torch.float32)
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        view = spectra[:, :nb * K]
+        eng.mtmfft(x[b0:b0 + nb], tapers, nfft, scale, polyremoval=pr, freq_idx=fidx, output="fourier_planar",
+                   keeptapers=True, out=view, freq_major=True)
+        ex.accumulate(view, alpha=1.0 / K, beta=0.0 if b0 == 0 else 1.0)
+    lo, hi = ex.f_begin[ex.rank], ex.f_begin[ex.rank + 1]
+    if ex.world == 1 or not gather:
+        out_dev = None
+        coh, _ = ex.finish(B, output=output, out=out_dev)
+        return _finish(coh[None], to_host, out_host), freqs[lo:hi]
+    # every rank wants the whole result: all-gather the normalised slabs (padded to the largest slab)
+    coh, _ = ex.finish(B, output=output)
+    nf_max = max(ex.f_begin[r + 1] - ex.f_begin[r] for r in range(ex.world))
+    pad = torch.zeros((nf_max, n_chan, n_chan), dtype=coh.dtype, device=eng.tdev)
+    pad[:hi - lo] = coh
+    full = torch.empty((ex.world, nf_max, n_chan, n_chan), dtype=coh.dtype, device=eng.tdev)
+    if coh.dtype == torch.complex64:
+        dist.all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(pad), group=reduce_group)
+    else:
+        dist.all_gather_into_tensor(full, pad, group=reduce_group)
+    res = torch.cat([full[r, :ex.f_begin[r + 1] - ex.f_begin[r]] for r in range(ex.world)], dim=0)[None]
+    return _finish(res, to_host, out_host), freqs
 
 
 def granger(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_opt=None, polyremoval=0,

@@ -108,6 +108,58 @@ int spyb_csd_accumulate_planar(const float* planes, long long sx_f, long long sx
     return csd_accumulate_tc(d, static_cast<cudaStream_t>(stream));
 }
 
+int spyb_csd_tile_count(int n_chan) { return csd_tile_count(n_chan); }
+
+int spyb_csd_accumulate_tiles(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                              int n_chan, float alpha, float beta, void* const* owner_base_host,
+                              const int* f_begin_host, int n_owners, int src_rank, void* stream) {
+    if (!owner_base_host || !f_begin_host) return fail("owner_base_host / f_begin_host must not be NULL");
+    CsdPlanarDesc d;
+    d.planes = planes; d.sx_f = sx_f; d.sx_r = sx_r;
+    d.n_rows = n_rows; d.n_freq = n_freq; d.n_chan = n_chan;
+    d.alpha = alpha; d.beta = beta; d.acc = nullptr;
+    return csd_accumulate_tc_tiles(d, owner_base_host, f_begin_host, n_owners, src_rank,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int spyb_csd_normalize_tiles(const void* slots, int n_src, int n_freq_local, int n_chan, float pre_scale,
+                             int out_kind, void* out, void* stream) {
+    if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
+    return csd_normalize_tiles(slots, n_src, n_freq_local, n_chan, pre_scale, out_kind, out,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int spyb_peer_alloc(long long bytes, void** ptr_out, unsigned char* handle64_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!ptr_out || !handle64_out || bytes <= 0) return fail("spyb_peer_alloc: bad arguments");
+    void* p = nullptr;
+    SPYB_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+    memcpy(handle64_out, &h, 64);
+    *ptr_out = p;
+    return 0;
+}
+
+int spyb_peer_open(const unsigned char* handle64, void** ptr_out) {
+    if (!ptr_out || !handle64) return fail("spyb_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SPYB_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int spyb_peer_close(void* mapped_ptr) {
+    SPYB_CUDA(cudaIpcCloseMemHandle(mapped_ptr));
+    return 0;
+}
+
+int spyb_peer_free(void* ptr) {
+    SPYB_CUDA(cudaFree(ptr));
+    return 0;
+}
+
 int spyb_csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind,
                        void* out, void* stream) {
     if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);

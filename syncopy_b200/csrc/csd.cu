@@ -296,6 +296,146 @@ int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Coherency straight from the "tile slots" the tcgen05 kernel fills (csd_tc.cu, store_mode 2):
+//   slots [n_src][n_freq][n_tiles][128][128] complex64, one slot set per source rank, upper tiles only.
+// Sums the source ranks (fixed order: deterministic), applies pre_scale (1 / nTrials), normalises with the
+// diagonal and writes the full Hermitian-consistent [n_freq][C][C] result: elements on / above the diagonal from
+// the tile, the mirrored ones as their conjugates (csd.py:118-172 on the trial average,
+// computational_routine.py:1022-1032 for the sum over ranks).
+// ---------------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void conv_store(void* out, long long idx, float2 c) {
+    if (KIND == OUT_FOURIER) reinterpret_cast<float2*>(out)[idx] = c;
+    else reinterpret_cast<float*>(out)[idx] = KIND == OUT_ABS ? sqrtf(c.x * c.x + c.y * c.y) : convert_real(c, KIND);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) csd_normalize_tiles_kernel(const float2* __restrict__ slots, int n_src,
+                                                                  long long src_stride, int n_tiles, int C,
+                                                                  float pre_scale, void* __restrict__ out) {
+    // block = 32 rows x 128 columns of one tile, walked as 32 x 32 chunks; the mirrored half of every chunk goes
+    // through a shared-memory transpose so that both halves are stored as 128-byte row pieces
+    __shared__ float2 s_di[32], s_dj[128];
+    __shared__ float s_ri[32], s_rj[128];
+    __shared__ float2 s_t[32][33];
+    __shared__ int s_general;
+    const int t = blockIdx.y, f = blockIdx.z;
+    const int ti = n_tiles == 1 ? 0 : (t >> 1), tj = n_tiles == 1 ? 0 : ((t + 1) >> 1);
+    const int bi = blockIdx.x;
+    const bool diag_tile = ti == tj;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const float2* __restrict__ fbase = slots + (long long)f * n_tiles * (128 * 128);
+    const float2* __restrict__ tile = fbase + t * (128 * 128);
+    if (tid == 0) s_general = 0;
+    __syncthreads();
+    if (tid < 160) {
+        const bool col = tid >= 32;
+        const int l = col ? tid - 32 : bi * 32 + tid;
+        const int tt = n_tiles == 1 ? 0 : ((col ? tj : ti) == 0 ? 0 : 2);
+        const float2* __restrict__ dt = fbase + tt * (128 * 128) + l * 129;
+        float2 d = make_float2(0.f, 0.f);
+        for (int sidx = 0; sidx < n_src; ++sidx) { const float2 w = __ldg(dt + sidx * src_stride); d.x += w.x; d.y += w.y; }
+        d.x *= pre_scale; d.y *= pre_scale;
+        const float rs = rsqrtf(d.x);
+        if (col) { s_dj[tid - 32] = d; s_rj[tid - 32] = rs; } else { s_di[tid] = d; s_ri[tid] = rs; }
+        if (d.y != 0.f || !(d.x > 0.f)) s_general = 1;
+    }
+    __syncthreads();
+    const bool general = s_general != 0;
+    const int I0 = ti * 128 + bi * 32;
+    float* __restrict__ outf = reinterpret_cast<float*>(out) + (long long)f * C * C * (KIND == OUT_FOURIER ? 2 : 1);
+    float2* __restrict__ outc = reinterpret_cast<float2*>(outf);
+
+    for (int bj = diag_tile ? bi : 0; bj < 4; ++bj) {            // chunks left of the diagonal are never read
+        const bool diag_blk = diag_tile && bi == bj;
+        const int J0 = tj * 128 + bj * 32;
+        float2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = make_float2(0.f, 0.f);
+        const float2* __restrict__ src = tile + (bi * 32 + ty) * 128 + bj * 32 + tx;
+        for (int sidx = 0; sidx < n_src; ++sidx) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 w = __ldg(src + k * (8 * 128));
+                v[k].x += w.x; v[k].y += w.y;
+            }
+            src += src_stride;
+        }
+        const float rsj = s_rj[bj * 32 + tx] * pre_scale;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = ty + 8 * k;
+            float2 c;
+            if (!general) {
+                const float w = s_ri[r] * rsj;
+                c = make_float2(v[k].x * w, v[k].y * w);
+                if (diag_blk && tx == r) c.y = 0.f;
+            } else {
+                const float2 x = make_float2(v[k].x * pre_scale, v[k].y * pre_scale);
+                const float2 den = csqrt_principal(cmul(s_di[r], s_dj[bj * 32 + tx]));
+                const float d2 = den.x * den.x + den.y * den.y;
+                c = make_float2((x.x * den.x + x.y * den.y) / d2, (x.y * den.x - x.x * den.y) / d2);
+            }
+            // convert once; the mirrored element is the converted conjugate (bit-identical magnitudes)
+            const int idx = (I0 + r) * C + J0 + tx;
+            if (KIND == OUT_FOURIER) {
+                if (!diag_blk || tx >= r) outc[idx] = c;
+                s_t[r][tx] = make_float2(c.x, -c.y);
+            } else {
+                float val;
+                if (KIND == OUT_ABS) { const float q = c.x * c.x + c.y * c.y; val = q > 0.f ? q * rsqrtf(q) : 0.f; }
+                else val = convert_real(c, KIND);
+                if (!diag_blk || tx >= r) outf[idx] = val;
+                s_t[r][tx].x = (KIND == OUT_IMAG || KIND == OUT_ANGLE) ? -val : val;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int jr = ty + 8 * k;                           // source column = output row
+            if (!diag_blk || jr > tx) {                          // source (i = tx, j = jr) strictly above the diagonal
+                const int idx = (J0 + jr) * C + I0 + tx;
+                if (KIND == OUT_FOURIER) outc[idx] = s_t[tx][jr];
+                else outf[idx] = s_t[tx][jr].x;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int KIND>
+static int launch_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, float pre_scale, void* out,
+                                  cudaStream_t stream) {
+    const int n_tiles = n_chan == 256 ? 3 : 1;
+    const long long src_stride = (long long)n_freq * n_tiles * 128 * 128;
+    dim3 grid(4, n_tiles, n_freq);
+    csd_normalize_tiles_kernel<KIND><<<grid, 256, 0, stream>>>(reinterpret_cast<const float2*>(slots), n_src, src_stride,
+                                                               n_tiles, n_chan, pre_scale, out);
+    SPYB_LAUNCH_CHECK("csd_normalize_tiles_kernel");
+    count_launch();
+    return 0;
+}
+
+int csd_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, float pre_scale, int out_kind,
+                        void* out, cudaStream_t stream) {
+    if (n_freq <= 0) return 0;
+    if (n_chan != 128 && n_chan != 256) return fail("tile slots exist for 128 or 256 channels only (got %d)", n_chan);
+    if (n_src < 1) return fail("csd_normalize_tiles: need at least one source slot");
+    if (n_freq > 65535) return fail("csd_normalize_tiles: more than 65535 frequencies per call are not supported");
+    switch (out_kind) {
+        case OUT_POW:     return launch_normalize_tiles<OUT_POW>(slots, n_src, n_freq, n_chan, pre_scale, out, stream);
+        case OUT_ABS:     return launch_normalize_tiles<OUT_ABS>(slots, n_src, n_freq, n_chan, pre_scale, out, stream);
+        case OUT_FOURIER: return launch_normalize_tiles<OUT_FOURIER>(slots, n_src, n_freq, n_chan, pre_scale, out, stream);
+        case OUT_REAL:    return launch_normalize_tiles<OUT_REAL>(slots, n_src, n_freq, n_chan, pre_scale, out, stream);
+        case OUT_IMAG:    return launch_normalize_tiles<OUT_IMAG>(slots, n_src, n_freq, n_chan, pre_scale, out, stream);
+        case OUT_ANGLE:   return launch_normalize_tiles<OUT_ANGLE>(slots, n_src, n_freq, n_chan, pre_scale, out, stream);
+        case OUT_ABSREAL: return launch_normalize_tiles<OUT_ABSREAL>(slots, n_src, n_freq, n_chan, pre_scale, out, stream);
+        case OUT_ABSIMAG: return launch_normalize_tiles<OUT_ABSIMAG>(slots, n_src, n_freq, n_chan, pre_scale, out, stream);
+        default:          return fail("bad out_kind %d", out_kind);
+    }
+}
+
 // in-place scale of a float buffer (trial mean: computational_routine.py:1030-1032)
 __global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;

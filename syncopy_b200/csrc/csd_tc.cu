@@ -43,6 +43,7 @@ constexpr int TC_PLANE = TC_KC * 512;  // bytes: one plane (128 channels x KC ro
 constexpr int TC_SLOT = 4 * TC_PLANE;  // half-tile: re_hi | im_hi | re_lo | im_lo
 constexpr int TC_STAGE = 2 * TC_SLOT;  // row-block half-tile (A) + column-block half-tile (B)
 constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_RANKS = 16;
 
 struct TcArgs {
     int n_rows, n_freq, n_chan;
@@ -51,7 +52,13 @@ struct TcArgs {
     int store_mode;            // 0: per-thread row stores (debug), 1: shared-memory transposed, coalesced
     int rewrite_hi;            // 1: store rna_tf32(x) back as the hi operand; 0: let the MMA truncate x itself
     float alpha, beta;
-    float2* acc;               // [n_freq][C][C]
+    float2* acc;               // [n_freq][C][C]   (store_mode 0 / 1)
+    // store_mode 2 ("tile slots"): every computed 128x128 tile goes, unmirrored, to the rank that owns its
+    // frequency -- plain stores through peer-mapped pointers, so the NVLink transfer of a finished tile overlaps
+    // the MMAs of the next one.  Slot layout at owner o: [src_rank][f - f_begin[o]][tile][128][128] complex64.
+    float2* owner_base[TC_MAX_RANKS];
+    int f_begin[TC_MAX_RANKS + 1];
+    int n_owners, src_rank;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -386,6 +393,33 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             float2* __restrict__ fmat = a.acc + (size_t)f * C * C;
             float2* stg = staging + (warp - 8) * (32 * 16);
             const bool diag_tile = ti == tj;
+            if (a.store_mode == 2) {
+                int o = 0;
+                while (o + 1 < a.n_owners && f >= a.f_begin[o + 1]) ++o;
+                const int nf_o = a.f_begin[o + 1] - a.f_begin[o];
+                const int t = item - f * a.n_tiles;
+                float2* __restrict__ tile = a.owner_base[o] +
+                    (((size_t)a.src_rank * nf_o + (size_t)(f - a.f_begin[o])) * a.n_tiles + t) * (128 * 128);
+                const int r0 = lane_grp * 32;                    // first tile row of this warp
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj)
+                        stg[lane * 16 + (jj ^ (lane & 15))] = make_float2(sr[c0 + jj] * a.alpha, si[c0 + jj] * a.alpha);
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 16; ++it) {
+                        const int r = 2 * it + (lane >> 4), cc = lane & 15;
+                        float2 o2 = stg[r * 16 + (cc ^ (r & 15))];
+                        float2* dst = tile + (size_t)(r0 + r) * 128 + chalf * 64 + c0 + cc;
+                        if (diag_tile && r0 + r == chalf * 64 + c0 + cc) o2.y = 0.f;    // auto-spectra are exactly real
+                        if (a.beta != 0.f) { const float2 old0 = *dst; o2.x += a.beta * old0.x; o2.y += a.beta * old0.y; }
+                        *dst = o2;
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
             if (a.store_mode == 0) {
                 float2* __restrict__ orow = fmat + (size_t)i * C;
 #pragma unroll
@@ -462,12 +496,12 @@ bool csd_tc_supported(int n_chan, long long sx_f, long long sx_r) {
     return (n_chan == 128 || n_chan == 256) && sx_r % 4 == 0 && sx_f % 4 == 0;
 }
 
-int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream) {
+static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     if (d.n_freq <= 0 || d.n_chan <= 0) return 0;
     if (!csd_tc_supported(d.n_chan, d.sx_f, d.sx_r))
         return fail("tcgen05 CSD kernel needs n_chan in {128, 256} and 16-byte aligned strides "
                     "(got n_chan=%d, sx_f=%lld, sx_r=%lld)", d.n_chan, d.sx_f, d.sx_r);
-    if (reinterpret_cast<uintptr_t>(d.planes) % 16 != 0 || reinterpret_cast<uintptr_t>(d.acc) % 16 != 0)
+    if (reinterpret_cast<uintptr_t>(d.planes) % 16 != 0)
         return fail("tcgen05 CSD kernel needs 16-byte aligned buffers");
     if (d.n_rows <= 0) return fail("csd: n_rows must be positive");
     EncodeTiledFn encode = get_encode_fn();
@@ -484,18 +518,14 @@ int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream) {
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code %d", (int)r);
 
-    TcArgs a;
     a.n_rows = d.n_rows; a.n_freq = d.n_freq; a.n_chan = C;
     a.n_tiles = C == 256 ? 3 : 1;
     a.alpha = d.alpha; a.beta = d.beta;
-    a.acc = reinterpret_cast<float2*>(d.acc);
     // accumulation-chain length in rows (multiple of TC_KC); SPYB_TC_CHAIN_ROWS overrides for experiments
     int chain_rows = 64;
     if (const char* e = getenv("SPYB_TC_CHAIN_ROWS")) chain_rows = atoi(e);
     if (chain_rows < TC_KC) chain_rows = TC_KC;
     a.chain_ksteps = chain_rows / TC_KC;
-    a.store_mode = 1;
-    if (const char* e = getenv("SPYB_TC_STORE")) a.store_mode = atoi(e);
     a.rewrite_hi = 1;
     if (const char* e = getenv("SPYB_TC_REWRITE_HI")) a.rewrite_hi = atoi(e) != 0;
     const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2);
@@ -514,6 +544,36 @@ int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream) {
     SPYB_LAUNCH_CHECK("csd_tc_kernel");
     count_launch();
     return 0;
+}
+
+int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream) {
+    if (reinterpret_cast<uintptr_t>(d.acc) % 16 != 0) return fail("tcgen05 CSD kernel needs 16-byte aligned buffers");
+    TcArgs a = {};
+    a.acc = reinterpret_cast<float2*>(d.acc);
+    a.store_mode = 1;
+    if (const char* e = getenv("SPYB_TC_STORE")) a.store_mode = atoi(e) != 0;
+    return launch_tc(d, a, stream);
+}
+
+int csd_tile_count(int n_chan) { return n_chan == 256 ? 3 : 1; }
+
+int csd_accumulate_tc_tiles(const CsdPlanarDesc& d, void* const* owner_base, const int* f_begin, int n_owners,
+                            int src_rank, cudaStream_t stream) {
+    if (n_owners < 1 || n_owners > TC_MAX_RANKS) return fail("tile slots: 1..%d owner ranks supported (got %d)", TC_MAX_RANKS, n_owners);
+    if (src_rank < 0) return fail("tile slots: bad source rank %d", src_rank);
+    if (f_begin[0] != 0 || f_begin[n_owners] != d.n_freq) return fail("tile slots: frequency slabs must cover [0, %d)", d.n_freq);
+    TcArgs a = {};
+    a.store_mode = 2;
+    a.n_owners = n_owners; a.src_rank = src_rank;
+    for (int o = 0; o < n_owners; ++o) {
+        if (f_begin[o + 1] < f_begin[o]) return fail("tile slots: frequency slabs must be ascending");
+        if (owner_base[o] == nullptr || reinterpret_cast<uintptr_t>(owner_base[o]) % 16 != 0)
+            return fail("tile slots: owner %d has no (aligned) slot buffer", o);
+        a.owner_base[o] = reinterpret_cast<float2*>(owner_base[o]);
+        a.f_begin[o] = f_begin[o];
+    }
+    a.f_begin[n_owners] = f_begin[n_owners];
+    return launch_tc(d, a, stream);
 }
 
 }  // namespace spyb

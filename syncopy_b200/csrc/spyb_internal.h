@@ -50,6 +50,13 @@ struct CsdPlanarDesc {
 };
 bool csd_tc_supported(int n_chan, long long sx_f, long long sx_r);
 int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream);
+// "tile slots": the upper 128x128 tiles of every frequency go, unmirrored, to the rank owning the frequency
+// (peer-mapped base pointers; d.acc is ignored); csd_normalize_tiles sums the source ranks and normalises
+int csd_tile_count(int n_chan);
+int csd_accumulate_tc_tiles(const CsdPlanarDesc& d, void* const* owner_base, const int* f_begin, int n_owners,
+                            int src_rank, cudaStream_t stream);
+int csd_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, float pre_scale, int out_kind,
+                        void* out, cudaStream_t stream);
 // Wavelet / superlet transforms as FFT convolutions (cwt.cu)
 struct CwtDesc {
     const void* xspec = nullptr;     // device complex64 [trial][L/2+1][chan], spectra of the zero-padded trials

@@ -9,6 +9,9 @@ here every rank accumulates its partial sum in HBM and one NCCL all-reduce (gloo
 tests) combines them.  Time-frequency results (keeptrials=True) need no collective at all:
 trial k's rows are disjoint (`trial_shard` gives the contiguous block of each rank).
 """
+import ctypes as C
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -31,3 +34,128 @@ def allreduce_csd(csd_sum, n_trials, group=None):
     cnt = torch.tensor([float(n_trials)], dtype=torch.float64, device=csd_sum.device)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     return int(round(cnt.item()))
+
+
+def freq_slabs(n_freq, world):
+    """Slab boundaries [f_0 = 0, ..., f_world = n_freq]: rank o owns the frequencies [f_o, f_{o+1})."""
+    return [trial_shard(n_freq, r, world)[0] for r in range(world)] + [n_freq]
+
+
+class _RawCuda:
+    """Zero-copy view of library-owned device memory for torch (`__cuda_array_interface__`)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class TileExchange:
+    """
+    The data path of the trial-averaged cross spectra on several GPUs, without a collective: every rank owns a slab
+    of frequencies and a slot buffer [world][nF_slab][n_tiles][128][128] complex64 that all ranks of the node can
+    write (CUDA IPC mapping, P2P over NVLink).  The tcgen05 contraction of rank r stores each finished upper tile
+    of frequency f straight into slot r of f's owner (`Engine.csd_accumulate_tiles`), so the exchange overlaps the
+    tensor-core work tile by tile; one small all-reduce of the trial counts doubles as the barrier; then every rank
+    sums the slots of its slab and normalises (`Engine.csd_normalize_tiles`).  Bytes crossing NVLink per rank:
+    (world-1)/world * 0.75 * |CSD| instead of 2 (world-1)/world * |CSD| for a ring all-reduce.
+
+    Two buffers alternate between calls: a rank that runs ahead can start filling buffer (k+1) % 2 while a
+    slower rank still reads buffer k % 2; passing the barrier of call k+1 implies everyone has finished call k.
+    """
+
+    def __init__(self, engine, n_freq, n_chan, group=None):
+        self.eng = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if group is not None else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.n_freq, self.n_chan = int(n_freq), int(n_chan)
+        self.n_tiles = engine.csd_tile_count(n_chan)
+        self.f_begin = freq_slabs(self.n_freq, self.world)
+        self.nf_local = self.f_begin[self.rank + 1] - self.f_begin[self.rank]
+        self.call = 0
+        shape = (self.world, max(self.nf_local, 1), self.n_tiles, 128, 128)
+        nbytes = int(np.prod(shape)) * 8
+        lib = engine.lib
+        self._own, self._mapped, self.slots, self.owner_ptrs = [], [], [], []
+        from . import _lib
+        for _ in range(2):
+            if self.world == 1:
+                buf = torch.empty(shape, dtype=torch.complex64, device=engine.tdev)
+                self.slots.append(buf)
+                self.owner_ptrs.append([buf.data_ptr()])
+                continue
+            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+            _lib.check(lib.spyb_peer_alloc(nbytes, C.byref(ptr), handle))
+            self._own.append(ptr.value)
+            raw = torch.as_tensor(_RawCuda(ptr.value, (int(np.prod(shape)) * 2,), "<f4"), device=engine.tdev)
+            self.slots.append(torch.view_as_complex(raw.view(-1, 2)).view(shape))
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, handle.raw, group=group)
+            ptrs = []
+            for r, h in enumerate(gathered):
+                if r == self.rank:
+                    ptrs.append(ptr.value)
+                else:
+                    mp = C.c_void_p()
+                    _lib.check(lib.spyb_peer_open(h, C.byref(mp)))
+                    self._mapped.append(mp.value)
+                    ptrs.append(mp.value)
+            self.owner_ptrs.append(ptrs)
+
+    def accumulate(self, planes, alpha=1.0, beta=0.0):
+        """Contraction of this rank's rows into everyone's slot buffers of the current call."""
+        k = self.call % 2
+        self.eng.csd_accumulate_tiles(planes, self.owner_ptrs[k], self.f_begin, self.rank, alpha, beta)
+
+    def barrier(self, n_trials, n_total=None):
+        """
+        All ranks have finished writing the current buffer once this (stream-ordered) all-reduce of the trial
+        counts completes.  Returns the global trial count; when the caller already knows it (`n_total`) the
+        result is not read back, so the host never waits for the device.
+        """
+        if self.world > 1:
+            if getattr(self, "_cnt", None) is None:
+                self._cnt = torch.empty(1, dtype=torch.float64, device=self.eng.tdev)
+            self._cnt.fill_(float(n_trials))
+            dist.all_reduce(self._cnt, op=dist.ReduceOp.SUM, group=self.group)
+            if n_total is None:
+                n_total = int(round(self._cnt.item()))
+        elif n_total is None:
+            n_total = n_trials
+        return n_total
+
+    def normalize(self, n_total, output="abs", out=None):
+        """Sum over the source ranks + coherency of the local slab [nF_slab, C, C]; ends the current call."""
+        k = self.call % 2
+        self.call += 1
+        if self.nf_local == 0:
+            return torch.empty((0, self.n_chan, self.n_chan), device=self.eng.tdev)
+        return self.eng.csd_normalize_tiles(self.slots[k][:, :self.nf_local], self.n_chan, output=output,
+                                            pre_scale=1.0 / n_total, out=out)
+
+    def finish(self, n_trials, output="abs", out=None, n_total=None):
+        n_total = self.barrier(n_trials, n_total)
+        return self.normalize(n_total, output=output, out=out), n_total
+
+    def close(self):
+        from . import _lib
+        torch.cuda.synchronize(self.eng.tdev)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for mp in self._mapped:
+            self.eng.lib.spyb_peer_close(mp)
+        self.slots = []
+        for p in self._own:
+            self.eng.lib.spyb_peer_free(p)
+        self._mapped, self._own = [], []
+
+
+_exchanges = {}
+
+
+def get_tile_exchange(engine, n_freq, n_chan, group=None):
+    """Process-wide cache: the IPC set-up is paid once per (shape, group)."""
+    key = (engine.device, int(n_freq), int(n_chan), id(group) if group is not None else None)
+    if key not in _exchanges:
+        _exchanges[key] = TileExchange(engine, n_freq, n_chan, group)
+    return _exchanges[key]

@@ -59,6 +59,17 @@ class Engine:
             self._tables[key] = self.to_device(tab.astype(np.float32))
         return self._tables[key]
 
+    def scratch(self, name, shape, dtype):
+        """Grow-only, reused device scratch tensor (e.g. the spectra handed from K1 to K2)."""
+        n = int(np.prod(shape))
+        key = ("scratch", name, dtype)
+        buf = self._tables.get(key)
+        if buf is None or buf.numel() < n:
+            self._tables[key] = None
+            buf = torch.empty(n, dtype=dtype, device=self.tdev)
+            self._tables[key] = buf
+        return buf[:n].view(shape)
+
     def index_table(self, idx):
         if idx is None:
             return None
@@ -179,6 +190,38 @@ class Engine:
             planes.data_ptr(), (planes.stride(0) if nF > 1 else 2 * R * Cn), 2 * Cn, R, nF, Cn,
             float(alpha), float(beta), acc.data_ptr(), self.stream()))
         return acc
+
+    def csd_tile_count(self, n_chan):
+        return int(self.lib.spyb_csd_tile_count(int(n_chan)))
+
+    def csd_accumulate_tiles(self, planes, owner_ptrs, f_begin, src_rank=0, alpha=1.0, beta=0.0):
+        """
+        planes [nF, R, 2, C] float32 -> the upper 128x128 tiles of sum_r X_r X_r^H, frequency f written into the
+        slot buffer of the rank owning f: `owner_ptrs[o]` is the (possibly peer-mapped) device address of rank o's
+        buffer [n_src, f_begin[o+1]-f_begin[o], n_tiles, 128, 128] complex64, this rank fills source slot `src_rank`.
+        """
+        import ctypes as C
+        assert planes.is_cuda and planes.dtype == torch.float32 and planes.dim() == 4 and planes.shape[2] == 2
+        nF, R, _, Cn = planes.shape
+        assert planes[0].is_contiguous() and len(f_begin) == len(owner_ptrs) + 1
+        n_own = len(owner_ptrs)
+        ptrs = (C.c_void_p * n_own)(*[int(p) for p in owner_ptrs])
+        fb = (C.c_int * (n_own + 1))(*[int(v) for v in f_begin])
+        _lib.check(self.lib.spyb_csd_accumulate_tiles(
+            planes.data_ptr(), (planes.stride(0) if nF > 1 else 2 * R * Cn), 2 * Cn, R, nF, Cn,
+            float(alpha), float(beta), ptrs, fb, n_own, int(src_rank), self.stream()))
+
+    def csd_normalize_tiles(self, slots, n_chan, output="abs", pre_scale=1.0, out=None):
+        """slots [n_src, nF_loc, n_tiles, 128, 128] complex64 (local) -> coherency [nF_loc, C, C] of the summed slots."""
+        assert slots.is_cuda and slots.dtype == torch.complex64 and slots.is_contiguous() and slots.dim() == 5
+        n_src, nF = slots.shape[0], slots.shape[1]
+        kind = hm.out_kind(output)
+        if out is None:
+            out = torch.empty((nF, n_chan, n_chan), dtype=_CDTYPE[kind == 2], device=self.tdev)
+        assert out.is_contiguous() and out.numel() == nF * n_chan * n_chan and out.dtype == _CDTYPE[kind == 2]
+        _lib.check(self.lib.spyb_csd_normalize_tiles(slots.data_ptr(), n_src, nF, int(n_chan), float(pre_scale), kind,
+                                                     out.data_ptr(), self.stream()))
+        return out
 
     def csd_normalize(self, csd, output="abs", pre_scale=1.0, out=None):
         """csd [..., C, C] complex64 -> coherency converted to `output` (same shape)."""

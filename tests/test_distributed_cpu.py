@@ -57,3 +57,13 @@ def test_allreduce_csd_gloo():
     trials = synth.white_noise(5, 64, 3)
     want = oc.trial_average([oc.cross_spectra_cF(t.copy(), 100., polyremoval=0)[0] for t in trials])[0]
     assert np.abs(total / n_tot - want).max() / np.abs(want).max() < 1e-6
+
+
+def test_freq_slabs_cover_the_axis():
+    from syncopy_b200.distributed import freq_slabs
+    for n_freq in (1, 5, 2049, 4097):
+        for world in (1, 2, 3, 8):
+            fb = freq_slabs(n_freq, world)
+            assert fb[0] == 0 and fb[-1] == n_freq and len(fb) == world + 1
+            sizes = [fb[i + 1] - fb[i] for i in range(world)]
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1

@@ -163,3 +163,72 @@ def test_tcgen05_csd_vs_oracle(engine, n_trials, n, c, taper, opt):
                                       out=S.clone())
     assert nerr(twice.csd_sum.cpu().numpy(), 2 * S.cpu().numpy()) <= 1e-6
     assert torch.isfinite(twice.csd_sum.abs()).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# "tile slot" path: upper tiles only, per-frequency-slab ownership, sum over source ranks + normalisation
+# ---------------------------------------------------------------------------------------------------------
+def _planar_spectra(engine, n_trials, n_samples, n_chan, taper, opt, seed=5):
+    import torch
+    from syncopy_b200 import hostmath as hm
+    x = torch.from_numpy(np.random.default_rng(seed).normal(size=(n_trials, n_samples, n_chan)).astype("f4")).to(engine.tdev)
+    tapers = engine.taper_table(taper, n_samples, n_samples, opt)
+    planes = engine.mtmfft(x, tapers, n_samples, hm.mtmfft_scale(n_samples, n_samples), polyremoval=0,
+                           output="fourier_planar", keeptapers=True, freq_major=True)
+    return planes, tapers.shape[0]
+
+
+@pytest.mark.parametrize("n_chan", [128, 256])
+@pytest.mark.parametrize("output", ["abs", "pow", "fourier", "imag", "angle"])
+def test_tile_path_matches_planar_path(engine, n_chan, output):
+    """one rank: accumulate_tiles + normalize_tiles == accumulate_planar + normalize (same sums, mirrored output)"""
+    import torch
+    planes, K = _planar_spectra(engine, 9, 256, n_chan, "dpss", {"NW": 2, "Kmax": 3})
+    nF = planes.shape[0]
+    csd = engine.csd_accumulate_planar(planes, alpha=1.0 / K)
+    want = engine.csd_normalize(csd[None], output=output, pre_scale=1.0 / 9)[0]
+    slots = torch.zeros((1, nF, engine.csd_tile_count(n_chan), 128, 128), dtype=torch.complex64, device=engine.tdev)
+    engine.csd_accumulate_tiles(planes, [slots.data_ptr()], [0, nF], 0, alpha=1.0 / K)
+    got = engine.csd_normalize_tiles(slots, n_chan, output=output, pre_scale=1.0 / 9)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if output == "angle":       # phases of numerically zero imaginary parts on the diagonal: compare as unit vectors
+        assert nerr(torch.polar(torch.ones_like(got), got).cpu().numpy(),
+                    torch.polar(torch.ones_like(want), want).cpu().numpy()) <= 2e-5
+    else:
+        assert nerr(got.cpu().numpy(), want.cpu().numpy()) <= 2e-6
+    if output in ("abs", "pow"):
+        assert torch.equal(got, got.transpose(1, 2))
+
+
+def test_tile_path_two_sources_and_slabs(engine):
+    """two source 'ranks' (trial shards) x two owners (frequency slabs), all on one GPU, chunked accumulation"""
+    import torch
+    n_chan, T = 256, 10
+    planes, K = _planar_spectra(engine, T, 128, n_chan, "hann", None, seed=9)
+    nF = planes.shape[0]
+    want = engine.csd_normalize(engine.csd_accumulate_planar(planes)[None], output="fourier", pre_scale=1.0 / T)[0]
+    f_begin = [0, 30, nF]
+    nt = engine.csd_tile_count(n_chan)
+    slabs = [torch.zeros((2, f_begin[o + 1] - f_begin[o], nt, 128, 128), dtype=torch.complex64, device=engine.tdev)
+             for o in range(2)]
+    ptrs = [s.data_ptr() for s in slabs]
+    rows = planes.shape[1]
+    half = (rows // 2)
+    # source 0: first half of the rows in two chunks (beta = 1 accumulates); source 1: the rest
+    engine.csd_accumulate_tiles(planes[:, :2], ptrs, f_begin, 0)
+    engine.csd_accumulate_tiles(planes[:, 2:half], ptrs, f_begin, 0, beta=1.0)
+    engine.csd_accumulate_tiles(planes[:, half:], ptrs, f_begin, 1)
+    got = torch.cat([engine.csd_normalize_tiles(slabs[o], n_chan, output="fourier", pre_scale=1.0 / T)
+                     for o in range(2)], dim=0)
+    assert nerr(got.cpu().numpy(), want.cpu().numpy()) <= 2e-6
+    assert (got - got.conj().transpose(1, 2)).abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("n_chan", [128, 256])
+def test_batched_coherence_tiles_vs_oracle(engine, n_chan):
+    from syncopy_b200 import batched
+    trials = synth.white_noise(5, 200, n_chan)
+    coh, freqs = batched.coherence(trials, 500., taper="hann", polyremoval=0, to_host=True)
+    av = oc.trial_average([oc.cross_spectra_cF(t.copy(), 500., taper="hann", polyremoval=0)[0] for t in trials])
+    assert coh.shape == (1, 101, n_chan, n_chan)
+    assert nerr(coh, oc.normalize_csd(av, "abs")) <= 2 * TOL

@@ -232,3 +232,18 @@ def test_batched_coherence_tiles_vs_oracle(engine, n_chan):
     av = oc.trial_average([oc.cross_spectra_cF(t.copy(), 500., taper="hann", polyremoval=0)[0] for t in trials])
     assert coh.shape == (1, 101, n_chan, n_chan)
     assert nerr(coh, oc.normalize_csd(av, "abs")) <= 2 * TOL
+
+
+def test_multi_gpu_tile_exchange_parity():
+    """Sharded coherence over 2 GPUs (peer tile stores) == single-GPU result; needs two visible GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run on a multi-GPU box: gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_gpu_check.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", script],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

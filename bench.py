@@ -232,6 +232,15 @@ class ClockSampler:
         return out
 
 
+def load_traffic(kernel, taper):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(f"{kernel}:{taper}")
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -399,7 +408,8 @@ def run_gpu_arm(args):
         achieved_tf = flops_alg / (csd_ms * 1e-3) / 1e12
         roofline = {
             "kernel": "csd contraction (K2, %s)" % ("CUDA-core FP32" if mode == "simt" else "tcgen05 3xTF32"), "bound": "tensor", "achieved": achieved_tf, "peak": tensor_peak,
-            "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved_tf / tensor_peak,
+            "traffic": load_traffic("csd_tc_kernel" if mode != "simt" else "csd_simt_kernel", args.taper),
             "peak_source": f"{peaks['source']} bf16 dense sustained (kernel timed inside a long step)",
             "algorithmic": f"8*C^2*nFreq*K flop per trial = {flops_alg / N_TRIALS / 1e9:.3f} GFLOP, x{N_TRIALS} trials/launch",
             "share_of_step": float(csd_ms / ms_per_step),

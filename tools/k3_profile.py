@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from syncopy_b200.engine import get_engine       # noqa: E402
 
 eng = get_engine(0)
-nF, R, C = 2049, 200, 256
+nF, R, C = 2049, int(os.environ.get("ROWS", "200")), 256
 planes = torch.randn((nF, R, 2, C), device=eng.tdev, dtype=torch.float32)
 slots = torch.zeros((1, nF, 3, 128, 128), dtype=torch.complex64, device=eng.tdev)
 out = torch.empty((nF, C, C), dtype=torch.float32, device=eng.tdev)

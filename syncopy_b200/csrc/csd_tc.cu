@@ -189,7 +189,9 @@ __device__ __forceinline__ void decode_item(int item, int n_tiles, int& f, int& 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared array (an integer round trip would demote every
+    // access below to generic LD / ST)
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)TC_STAGES * TC_STAGE);
     uint64_t* full_raw = bars;                      // [stage]  TMA landed
     uint64_t* full_conv = bars + TC_STAGES;         // [stage]  hi / lo split done

@@ -59,6 +59,7 @@ struct TcArgs {
     float2* owner_base[TC_MAX_RANKS];
     int f_begin[TC_MAX_RANKS + 1];
     int n_owners, src_rank;
+    int f_rot;                 // first frequency this rank works on (0 outside tile-slot mode)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -179,9 +180,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
 
 // Work item = (frequency f, upper-triangular 128x128 output tile (ti, tj)); items of one frequency are
 // neighbours in the persistent round-robin, so their operand tiles are shared through L2.
-__device__ __forceinline__ void decode_item(int item, int n_tiles, int& f, int& ti, int& tj) {
-    f = item / n_tiles;
-    const int t = item - f * n_tiles;
+// `f_rot` rotates the frequency order per rank (tile-slot mode): rank r starts with the slab of owner r+1 and ends
+// with its own, so at any moment the ranks of a node write to different owners instead of all to the same one.
+__device__ __forceinline__ void decode_item(int item, int n_tiles, int f_rot, int n_freq, int& f, int& ti, int& tj) {
+    const int fl = item / n_tiles;
+    const int t = item - fl * n_tiles;
+    f = fl + f_rot;
+    if (f >= n_freq) f -= n_freq;
     ti = t >> 1;            // 0 -> (0,0), 1 -> (0,1), 2 -> (1,1)
     tj = (t + 1) >> 1;
 }
@@ -234,7 +239,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 uint32_t phase = 0;
                 for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                     int f, ti, tj;
-                    decode_item(item, a.n_tiles, f, ti, tj);
+                    decode_item(item, a.n_tiles, a.f_rot, a.n_freq, f, ti, tj);
                     const int n_slots = ti == tj ? 1 : 2;
                     for (int ks = 0; ks < n_ksteps; ++ks) {
                         mbar_wait(&empty[s], phase ^ 1u);
@@ -259,7 +264,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             uint32_t phase = 0, chain = 0;               // chain counts accumulation chains over all items
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int f, ti, tj;
-                decode_item(item, a.n_tiles, f, ti, tj);
+                decode_item(item, a.n_tiles, a.f_rot, a.n_freq, f, ti, tj);
                 const uint32_t b_slot = ti == tj ? 0u : (uint32_t)TC_SLOT;
                 for (int ks = 0; ks < n_ksteps; ++ks) {
                     const int kc = ks % chain_ksteps;                  // position inside the accumulation chain
@@ -318,7 +323,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         uint32_t phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int f, ti, tj;
-            decode_item(item, a.n_tiles, f, ti, tj);
+            decode_item(item, a.n_tiles, a.f_rot, a.n_freq, f, ti, tj);
             const int n_slots = ti == tj ? 1 : 2;
             for (int ks = 0; ks < n_ksteps; ++ks) {
                 mbar_wait(&full_raw[s], phase);
@@ -361,7 +366,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         uint32_t chain = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int f, ti, tj;
-            decode_item(item, a.n_tiles, f, ti, tj);
+            decode_item(item, a.n_tiles, a.f_rot, a.n_freq, f, ti, tj);
             float sr[64], si[64];
 #pragma unroll
             for (int c = 0; c < 64; ++c) { sr[c] = 0.f; si[c] = 0.f; }
@@ -399,12 +404,14 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 int o = 0;
                 while (o + 1 < a.n_owners && f >= a.f_begin[o + 1]) ++o;
                 const int nf_o = a.f_begin[o + 1] - a.f_begin[o];
-                const int t = item - f * a.n_tiles;
+                const int t = item % a.n_tiles;
                 float2* __restrict__ tile = a.owner_base[o] +
                     (((size_t)a.src_rank * nf_o + (size_t)(f - a.f_begin[o])) * a.n_tiles + t) * (128 * 128);
                 const int r0 = lane_grp * 32;                    // first tile row of this warp
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 16) {
+                    // diagonal tiles: 16-column pieces entirely below the diagonal are never read (warp-uniform)
+                    if (diag_tile && chalf * 64 + c0 + 15 < r0) continue;
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj)
                         stg[lane * 16 + (jj ^ (lane & 15))] = make_float2(sr[c0 + jj] * a.alpha, si[c0 + jj] * a.alpha);
@@ -575,6 +582,7 @@ int csd_accumulate_tc_tiles(const CsdPlanarDesc& d, void* const* owner_base, con
         a.f_begin[o] = f_begin[o];
     }
     a.f_begin[n_owners] = f_begin[n_owners];
+    a.f_rot = n_owners > 1 ? f_begin[(src_rank + 1) % n_owners] % d.n_freq : 0;
     return launch_tc(d, a, stream);
 }
 

@@ -25,6 +25,7 @@ struct MtmArgs {
     int vec_in, vec_out;       // alignment allows 8-byte input loads / paired output stores
     int vec16;                 // alignment allows 16-byte asynchronous row copies (n_chan % 4 == 0, 16-byte aligned base)
     const float2* tw_dif;      // pass twiddles of the in-place DIF passes
+    int acc_smem;              // mtm_dif: the taper mean (keeptapers = 0) accumulates in shared memory, one store at the end
     float* chan_amax;          // optional [n_chan]: running max(|re|,|im|) of the scaled spectrum
     const float2* tw;
     const float2* chirp;

@@ -118,7 +118,7 @@ __device__ __forceinline__ void pair_reduce(float (&val)[NV], float* red, int ti
     }
 }
 
-template <int LOG2N, int P, int THREADS, int MINB>
+template <int LOG2N, int P, int THREADS, int MINB, bool ACC>
 __global__ void __launch_bounds__(THREADS, MINB) mtm_dif_kernel(const MtmArgs a) {
     constexpr int N = 1 << LOG2N;
     constexpr int STRIDE0 = N / 16;
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mtm_dif_kernel(const MtmArgs a)
     const bool vec_tile = P >= 2 && a.vec16 && full_tile;
     constexpr int CH = P >= 2 ? P / 2 : 1;                          // 16-byte chunks per row
     constexpr int RED_PER_WARP = CH * 8 > P * 4 ? CH * 8 : P * 4;
+    float* accb = red + (THREADS / 32) * RED_PER_WARP + 4 * P;      // taper-mean accumulators (acc_smem)
     auto load_tile = [&](float (&sums)[8], const bool with_sums) {
         if (vec_tile) {
             const int h = tid % CH;
@@ -300,6 +301,34 @@ __global__ void __launch_bounds__(THREADS, MINB) mtm_dif_kernel(const MtmArgs a)
             const float2 xb = make_float2((z1.y + z2.y) * half_scale, (z2.x - z1.x) * half_scale);
             amax_a = fmaxf(amax_a, fmaxf(fabsf(xa.x), fabsf(xa.y)));
             amax_b = fmaxf(amax_b, fmaxf(fabsf(xb.x), fabsf(xb.y)));
+            if constexpr (ACC) {
+                // taper mean without read-modify-write of the result: every thread revisits the same items for
+                // every taper, so its running sums live in its own shared-memory slots
+                if (a.out_kind == OUT_FOURIER) {
+                    float4* ap = reinterpret_cast<float4*>(accb) + item;
+                    float4 v = make_float4(xa.x, xa.y, xb.x, xb.y);
+                    if (k > 0) { const float4 old = *ap; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+                    if (k < a.n_tapers - 1) { *ap = v; continue; }
+                    if (!ca_ok) continue;
+                    float2* o = reinterpret_cast<float2*>(a.out) + off0 + (long long)fi * a.so_freq;
+                    o[0] = make_float2(v.x * inv_ntap, v.y * inv_ntap);
+                    if (cb_ok) o[1] = make_float2(v.z * inv_ntap, v.w * inv_ntap);
+                } else {
+                    float2* ap = reinterpret_cast<float2*>(accb) + item;
+                    float2 v = make_float2(convert_real(xa, a.out_kind), convert_real(xb, a.out_kind));
+                    if (k > 0) { const float2 old = *ap; v.x += old.x; v.y += old.y; }
+                    if (k < a.n_tapers - 1) { *ap = v; continue; }
+                    if (!ca_ok) continue;
+                    float* o = reinterpret_cast<float*>(a.out) + off0 + (long long)fi * a.so_freq;
+                    if (a.vec_out && cb_ok) {
+                        *reinterpret_cast<float2*>(o) = make_float2(v.x * inv_ntap, v.y * inv_ntap);
+                    } else {
+                        o[0] = v.x * inv_ntap;
+                        if (cb_ok) o[1] = v.y * inv_ntap;
+                    }
+                }
+                continue;
+            }
             if (!ca_ok) continue;
             const long long off = off0 + (long long)fi * a.so_freq;
             if (a.out_kind == OUT_FOURIER_PLANAR) {
@@ -367,17 +396,27 @@ __global__ void __launch_bounds__(THREADS, MINB) mtm_dif_kernel(const MtmArgs a)
 }
 
 template <int LOG2N, int P, int THREADS, int MINB>
-int launch_dif(const MtmArgs& a, cudaStream_t stream) {
+int launch_dif(const MtmArgs& a_in, cudaStream_t stream) {
     constexpr int N = 1 << LOG2N;
-    auto kern = mtm_dif_kernel<LOG2N, P, THREADS, MINB>;
     constexpr int CH = P >= 2 ? P / 2 : 1;
     constexpr int RED_PER_WARP = CH * 8 > P * 4 ? CH * 8 : P * 4;
-    const size_t smem = (size_t)N * P * sizeof(float2) + (size_t)(THREADS / 32) * RED_PER_WARP * sizeof(float) +
-                        (size_t)4 * P * sizeof(float) + 16;
-    static bool configured = false;   // per template instantiation
-    if (!configured) {
-        SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    constexpr size_t kMaxSmem = 227 * 1024;
+    size_t smem = (size_t)N * P * sizeof(float2) + (size_t)(THREADS / 32) * RED_PER_WARP * sizeof(float) +
+                  (size_t)4 * P * sizeof(float) + 16;
+    MtmArgs a = a_in;
+    a.acc_smem = 0;
+    if (!a.keeptapers && a.n_tapers > 1 && a.out_kind != OUT_FOURIER_PLANAR) {
+        const size_t acc = (size_t)a.n_freq_out * P * (a.out_kind == OUT_FOURIER ? 16 : 8) + 16;
+        if (smem + acc <= kMaxSmem) {
+            smem = ((smem + 15) & ~(size_t)15) + acc;
+            a.acc_smem = 1;
+        }
+    }
+    auto kern = a.acc_smem ? mtm_dif_kernel<LOG2N, P, THREADS, MINB, true> : mtm_dif_kernel<LOG2N, P, THREADS, MINB, false>;
+    static bool configured[2] = {false, false};   // per template instantiation
+    if (!configured[a.acc_smem]) {
+        SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        configured[a.acc_smem] = true;
     }
     const int chan_tiles = (a.n_chan + 2 * P - 1) / (2 * P);
     if (a.n_frames > 65535 || a.n_trials > 65535)

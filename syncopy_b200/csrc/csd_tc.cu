@@ -29,6 +29,8 @@
 
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "spyb_internal.h"
 
@@ -51,6 +53,7 @@ struct TcArgs {
     int chain_ksteps;          // pipeline stages (of TC_KC rows) accumulated in TMEM before the FP32 flush
     int store_mode;            // 0: per-thread row stores (debug), 1: shared-memory transposed, coalesced
     int rewrite_hi;            // 1: store rna_tf32(x) back as the hi operand; 0: let the MMA truncate x itself
+    int bf16_cross;            // 1: the cross terms hi*lo + lo*hi run as BF16 MMAs (K = 16) on bf16 copies of hi / lo
     float alpha, beta;
     float2* acc;               // [n_freq][C][C]   (store_mode 0 / 1)
     // store_mode 2 ("tile slots"): every computed 128x128 tile goes, unmirrored, to the rank that owns its
@@ -137,6 +140,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -171,6 +182,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
     d |= (uint64_t)1 << 61;     // SWIZZLE_128B_BASE32B
     return d;
+}
+// MN-major 16-bit operands, SWIZZLE_128B: canonical layout ((8,m),(8,k)) : ((16 B, LBO),(128 B, SBO)) -- 64 channels
+// (128 B) x 8 rows per 1 KB atom, 16-byte chunks XOR-ed with the row index; LBO = stride between 64-channel
+// blocks, SBO = stride between 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: BF16 x BF16 -> F32 (kind::f16), both operands MN-major, K = 16.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool neg_a) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((neg_a ? 1u : 0u) << 13) | (1u << 15) | (1u << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // Instruction descriptor: TF32 x TF32 -> F32, both operands MN-major.
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
@@ -279,6 +307,44 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                     if (elect_one()) {
                         const uint32_t d_re = tmem_base + buf * 256u, d_im = d_re + 128u;
                         const uint32_t st = smem_u32(base + (size_t)s * TC_STAGE);
+                        if (a.bf16_cross) {
+                            // slot: re_hi32 | im_hi32 | re_h16 | im_h16 | re_l16 | im_l16   (8 + 8 + 4 x 4 KB)
+                            constexpr uint32_t H16 = 2 * TC_PLANE, P16 = TC_PLANE / 2;
+                            constexpr uint32_t lbo16 = 2048u, sbo16 = 1024u;
+                            constexpr uint32_t ib_pos = make_idesc_bf16(128, 128, false);
+                            constexpr uint32_t ib_neg = make_idesc_bf16(128, 128, true);
+                            const uint32_t sa = st, sb = st + b_slot;
+                            const uint64_t Are_h = make_smem_desc_sw128(sa + H16, lbo16, sbo16);
+                            const uint64_t Aim_h = make_smem_desc_sw128(sa + H16 + P16, lbo16, sbo16);
+                            const uint64_t Are_l = make_smem_desc_sw128(sa + H16 + 2 * P16, lbo16, sbo16);
+                            const uint64_t Aim_l = make_smem_desc_sw128(sa + H16 + 3 * P16, lbo16, sbo16);
+                            const uint64_t Bre_h = make_smem_desc_sw128(sb + H16, lbo16, sbo16);
+                            const uint64_t Bim_h = make_smem_desc_sw128(sb + H16 + P16, lbo16, sbo16);
+                            const uint64_t Bre_l = make_smem_desc_sw128(sb + H16 + 2 * P16, lbo16, sbo16);
+                            const uint64_t Bim_l = make_smem_desc_sw128(sb + H16 + 3 * P16, lbo16, sbo16);
+                            const uint32_t first = kc > 0 ? 1u : 0u;
+                            // cross terms first (small addends), K = 16 rows per instruction
+                            umma_bf16(d_re, Are_l, Bre_h, ib_pos, first);
+                            umma_bf16(d_re, Are_h, Bre_l, ib_pos, 1u);
+                            umma_bf16(d_re, Aim_l, Bim_h, ib_pos, 1u);
+                            umma_bf16(d_re, Aim_h, Bim_l, ib_pos, 1u);
+                            umma_bf16(d_im, Aim_l, Bre_h, ib_pos, first);
+                            umma_bf16(d_im, Aim_h, Bre_l, ib_pos, 1u);
+                            umma_bf16(d_im, Are_l, Bim_h, ib_neg, 1u);
+                            umma_bf16(d_im, Are_h, Bim_l, ib_neg, 1u);
+#pragma unroll
+                            for (int kk = 0; kk < TC_KC / 8; ++kk) {
+                                const uint32_t ka = st + (uint32_t)kk * 1024u, kb = ka + b_slot;
+                                const uint64_t Are_hi = make_smem_desc(ka, lbo, sbo);
+                                const uint64_t Aim_hi = make_smem_desc(ka + TC_PLANE, lbo, sbo);
+                                const uint64_t Bre_hi = make_smem_desc(kb, lbo, sbo);
+                                const uint64_t Bim_hi = make_smem_desc(kb + TC_PLANE, lbo, sbo);
+                                umma_tf32(d_re, Are_hi, Bre_hi, idesc_pos, 1u);
+                                umma_tf32(d_re, Aim_hi, Bim_hi, idesc_pos, 1u);
+                                umma_tf32(d_im, Aim_hi, Bre_hi, idesc_pos, 1u);
+                                umma_tf32(d_im, Are_hi, Bim_hi, idesc_neg, 1u);
+                            }
+                        } else
 #pragma unroll
                         for (int kk = 0; kk < TC_KC / 8; ++kk) {
                             const uint32_t ka = st + (uint32_t)kk * 1024u, kb = ka + b_slot;
@@ -330,6 +396,41 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 for (int sl = 0; sl < n_slots; ++sl) {
                     float4* hi = reinterpret_cast<float4*>(base + (size_t)s * TC_STAGE + (size_t)sl * TC_SLOT);
                     float4* lo = hi + (2 * TC_PLANE) / 16;
+                    if (a.bf16_cross) {
+                        // fp32 planes are in the TMA layout: offset = c_blk*2048 + row*128 + c_in*4 with the 32-byte
+                        // chunk index XOR-ed with row % 4; the bf16 copies go to the SWIZZLE_128B MN-major layout:
+                        // blk64*2048 + (row/8)*1024 + (row%8)*128 + ((c%64/8) ^ (row%8))*16 + (c%8)*2
+                        uint8_t* h16 = reinterpret_cast<uint8_t*>(hi) + 2 * TC_PLANE;
+#pragma unroll 4
+                        for (int q = ct; q < (2 * TC_PLANE) / 16; q += TC_CONV_THREADS) {
+                            const float4 x = hi[q];
+                            float4 h;
+                            if (a.rewrite_hi) {
+                                h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+                                hi[q] = h;
+                            } else {                             // the tensor core ignores the low 13 mantissa bits
+                                h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                                h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                                h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                                h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                            }
+                            const uint32_t pl = (uint32_t)q / (TC_PLANE / 16);               // 0 re, 1 im
+                            const uint32_t phi = ((uint32_t)q % (TC_PLANE / 16)) * 16u;
+                            const uint32_t lin = phi ^ (((phi >> 7) & 3u) << 5);
+                            const uint32_t c = ((lin >> 11) << 5) | ((lin >> 2) & 31u), row = (lin >> 7) & 15u;
+                            const uint32_t off = ((c >> 6) << 11) | ((row >> 3) << 10) | ((row & 7u) << 7) |
+                                                 ((((c >> 3) & 7u) ^ (row & 7u)) << 4) | ((c & 7u) << 1);
+                            __nv_bfloat162 a0 = __floats2bfloat162_rn(h.x, h.y), a1 = __floats2bfloat162_rn(h.z, h.w);
+                            __nv_bfloat162 l0 = __floats2bfloat162_rn(x.x - h.x, x.y - h.y);
+                            __nv_bfloat162 l1 = __floats2bfloat162_rn(x.z - h.z, x.w - h.w);
+                            uint2 hv, lv;
+                            hv.x = *reinterpret_cast<uint32_t*>(&a0); hv.y = *reinterpret_cast<uint32_t*>(&a1);
+                            lv.x = *reinterpret_cast<uint32_t*>(&l0); lv.y = *reinterpret_cast<uint32_t*>(&l1);
+                            *reinterpret_cast<uint2*>(h16 + pl * (TC_PLANE / 2) + off) = hv;
+                            *reinterpret_cast<uint2*>(h16 + (2 + pl) * (TC_PLANE / 2) + off) = lv;
+                        }
+                        continue;
+                    }
 #pragma unroll 4
                     for (int q = ct; q < (2 * TC_PLANE) / 16; q += TC_CONV_THREADS) {
                         const float4 x = hi[q];
@@ -537,6 +638,9 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     a.chain_ksteps = chain_rows / TC_KC;
     a.rewrite_hi = 1;
     if (const char* e = getenv("SPYB_TC_REWRITE_HI")) a.rewrite_hi = atoi(e) != 0;
+    // cross terms as BF16 MMAs by default (1.1e-6 vs FP64, all-TF32: 1.3e-6); SPYB_TC_BF16=0 selects 3xTF32
+    a.bf16_cross = 1;
+    if (const char* e = getenv("SPYB_TC_BF16")) a.bf16_cross = atoi(e) != 0;
     const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2);
 
     static bool configured = false;

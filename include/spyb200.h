@@ -121,6 +121,15 @@ int spyb_csd_accumulate_planar(const float* planes, long long sx_f, long long sx
  * ever materialising the mirrored CSD.  Eligibility as spyb_csd_planar_supported.
  */
 int spyb_csd_tile_count(int n_chan);
+/*
+ * One rank, all (trial, taper) rows in one launch: cross-spectral sum (csd.py:98-102, computational_routine.py:1022-1032),
+ * coherency normalisation and output conversion (csd.py:118-172) in ONE kernel -- the epilogue of the tcgen05
+ * contraction divides by sqrt(C_ii C_jj) and writes out [n_freq][n_chan][n_chan] (float32, or complex64 for
+ * out_kind 2) including the mirrored half; the cross-spectral matrix never reaches memory (coherency does not
+ * depend on the 1/nTapers, 1/nTrials factors).  Same eligibility as spyb_csd_planar_supported.
+ */
+int spyb_csd_coherence_planar(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                              int n_chan, int out_kind, void* out, void* stream);
 int spyb_csd_accumulate_tiles(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
                               int n_chan, float alpha, float beta, void* const* owner_base_host,
                               const int* f_begin_host, int n_owners, int src_rank, void* stream);

@@ -241,9 +241,15 @@ def _coherence_tiles(eng, trials, samplerate, nSamples, foi, taper, taper_opt, p
     K = tapers.shape[0]
     scale = hm.mtmfft_scale(n_sig, nfft)
     pr = hm.polyremoval_code(polyremoval)
-    ex = get_tile_exchange(eng, n_freq, n_chan, reduce_group)
     chunk = max(1, min(B, MAX_SPECTRA_BYTES // max(1, n_freq * K * n_chan * 8)))
     spectra = eng.scratch("planar_spectra", (n_freq, min(chunk, B) * K, 2, n_chan), torch.float32)
+    if reduce_group is None and chunk >= B and not os.environ.get("SPYB_NO_FUSED_COH"):
+        # one rank, all rows in one launch: the contraction's epilogue normalises and mirrors (2 kernels in total)
+        eng.mtmfft(x, tapers, nfft, scale, polyremoval=pr, freq_idx=fidx, output="fourier_planar",
+                   keeptapers=True, out=spectra, freq_major=True)
+        coh = eng.csd_coherence_planar(spectra, output=output)
+        return _finish(coh[None], to_host, out_host), freqs
+    ex = get_tile_exchange(eng, n_freq, n_chan, reduce_group)
     for b0 in range(0, B, chunk):
         nb = min(chunk, B - b0)
         view = spectra[:, :nb * K]

@@ -110,6 +110,16 @@ int spyb_csd_accumulate_planar(const float* planes, long long sx_f, long long sx
 
 int spyb_csd_tile_count(int n_chan) { return csd_tile_count(n_chan); }
 
+int spyb_csd_coherence_planar(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                              int n_chan, int out_kind, void* out, void* stream) {
+    if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
+    CsdPlanarDesc d;
+    d.planes = planes; d.sx_f = sx_f; d.sx_r = sx_r;
+    d.n_rows = n_rows; d.n_freq = n_freq; d.n_chan = n_chan;
+    d.alpha = 1.f; d.beta = 0.f; d.acc = nullptr;
+    return csd_coherence_tc(d, out_kind, out, static_cast<cudaStream_t>(stream));
+}
+
 int spyb_csd_accumulate_tiles(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
                               int n_chan, float alpha, float beta, void* const* owner_base_host,
                               const int* f_begin_host, int n_owners, int src_rank, void* stream) {

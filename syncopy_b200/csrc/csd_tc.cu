@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include <cuda_bf16.h>
 
@@ -63,6 +64,11 @@ struct TcArgs {
     int f_begin[TC_MAX_RANKS + 1];
     int n_owners, src_rank;
     int f_rot;                 // first frequency this rank works on (0 outside tile-slot mode)
+    // store_mode 3 ("fused coherence", one rank, all rows in one launch): the epilogue normalises with the
+    // diagonal and writes the converted coherency [n_freq][C][C] (float32, or complex64 for out_kind 2) including
+    // the mirrored half; the cross-spectral matrix itself never reaches memory (csd.py:118-172 fused into the sum)
+    void* coh_out;
+    int out_kind;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -206,18 +212,43 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Work item = (frequency f, upper-triangular 128x128 output tile (ti, tj)); items of one frequency are
-// neighbours in the persistent round-robin, so their operand tiles are shared through L2.
-// `f_rot` rotates the frequency order per rank (tile-slot mode): rank r starts with the slab of owner r+1 and ends
-// with its own, so at any moment the ranks of a node write to different owners instead of all to the same one.
-__device__ __forceinline__ void decode_item(int item, int n_tiles, int f_rot, int n_freq, int& f, int& ti, int& tj) {
-    const int fl = item / n_tiles;
-    const int t = item - fl * n_tiles;
-    f = fl + f_rot;
-    if (f >= n_freq) f -= n_freq;
-    ti = t >> 1;            // 0 -> (0,0), 1 -> (0,1), 2 -> (1,1)
-    tj = (t + 1) >> 1;
-}
+// Work item = (frequency f, upper-triangular 128x128 output tile (ti, tj)).  A CTA enumerates its items with
+// k = 0 .. item_count-1:
+//   store_mode 0-2: item = blockIdx.x + k * gridDim.x over (f, t) with t fastest, so the items of one frequency are
+//     neighbours in the persistent round-robin and share their operand tiles through L2; in tile-slot mode `f_rot`
+//     rotates the frequency order per rank (rank r starts with the slab of owner r+1 and ends with its own), so at
+//     any moment the ranks of a node write to different owners instead of all to the same one;
+//   store_mode 3 (fused coherence): a CTA owns whole frequencies f = blockIdx.x + m * gridDim.x and runs their
+//     tiles back to back in the order (0,0), (1,1), (0,1): both diagonals are known when the off-diagonal tile ends.
+// t encodes the tile: 0 -> (0,0), 1 -> (0,1), 2 -> (1,1).
+struct ItemIter {
+    int n_tiles, n_freq, f_rot, fused, count;
+    __device__ __forceinline__ ItemIter(const TcArgs& a)
+        : n_tiles(a.n_tiles), n_freq(a.n_freq), f_rot(a.f_rot), fused(a.store_mode == 3) {
+        if (fused) {
+            const int mf = ((int)blockIdx.x < n_freq) ? (n_freq - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            count = mf * n_tiles;
+        } else {
+            const int n_items = n_freq * n_tiles;
+            count = ((int)blockIdx.x < n_items) ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        }
+    }
+    __device__ __forceinline__ void decode(int k, int& f, int& ti, int& tj, int& t) const {
+        if (fused) {
+            const int m = k / n_tiles, idx = k - m * n_tiles;
+            f = (int)blockIdx.x + m * (int)gridDim.x;
+            t = n_tiles == 1 ? 0 : (idx == 0 ? 0 : (idx == 1 ? 2 : 1));
+        } else {
+            const int item = (int)blockIdx.x + k * (int)gridDim.x;
+            const int fl = item / n_tiles;
+            t = item - fl * n_tiles;
+            f = fl + f_rot;
+            if (f >= n_freq) f -= n_freq;
+        }
+        ti = t >> 1;
+        tj = (t + 1) >> 1;
+    }
+};
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
@@ -236,7 +267,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = a.n_chan;
-    const int n_items = a.n_freq * a.n_tiles;
+    const ItemIter items(a);
     const int n_ksteps = (a.n_rows + TC_KC - 1) / TC_KC;
     const int chain_ksteps = a.chain_ksteps;
 
@@ -265,9 +296,9 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             if (elect_one()) {
                 int s = 0;
                 uint32_t phase = 0;
-                for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                    int f, ti, tj;
-                    decode_item(item, a.n_tiles, a.f_rot, a.n_freq, f, ti, tj);
+                for (int item = 0; item < items.count; ++item) {
+                    int f, ti, tj, t;
+                    items.decode(item, f, ti, tj, t);
                     const int n_slots = ti == tj ? 1 : 2;
                     for (int ks = 0; ks < n_ksteps; ++ks) {
                         mbar_wait(&empty[s], phase ^ 1u);
@@ -290,9 +321,9 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             constexpr uint32_t idesc_neg = make_idesc(128, 128, true);
             int s = 0;
             uint32_t phase = 0, chain = 0;               // chain counts accumulation chains over all items
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int f, ti, tj;
-                decode_item(item, a.n_tiles, a.f_rot, a.n_freq, f, ti, tj);
+            for (int item = 0; item < items.count; ++item) {
+                int f, ti, tj, t;
+                items.decode(item, f, ti, tj, t);
                 const uint32_t b_slot = ti == tj ? 0u : (uint32_t)TC_SLOT;
                 for (int ks = 0; ks < n_ksteps; ++ks) {
                     const int kc = ks % chain_ksteps;                  // position inside the accumulation chain
@@ -387,9 +418,9 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         const int ct = threadIdx.x - 128;                       // 0..127
         int s = 0;
         uint32_t phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int f, ti, tj;
-            decode_item(item, a.n_tiles, a.f_rot, a.n_freq, f, ti, tj);
+        for (int item = 0; item < items.count; ++item) {
+            int f, ti, tj, t;
+            items.decode(item, f, ti, tj, t);
             const int n_slots = ti == tj ? 1 : 2;
             for (int ks = 0; ks < n_ksteps; ++ks) {
                 mbar_wait(&full_raw[s], phase);
@@ -465,9 +496,9 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         const int lane_grp = warp & 3;                          // TMEM lanes this warp may read
         const int chalf = (warp - 8) >> 2;                      // which 64 columns
         uint32_t chain = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int f, ti, tj;
-            decode_item(item, a.n_tiles, a.f_rot, a.n_freq, f, ti, tj);
+        for (int item = 0; item < items.count; ++item) {
+            int f, ti, tj, t;
+            items.decode(item, f, ti, tj, t);
             float sr[64], si[64];
 #pragma unroll
             for (int c = 0; c < 64; ++c) { sr[c] = 0.f; si[c] = 0.f; }
@@ -501,11 +532,103 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             float2* __restrict__ fmat = a.acc + (size_t)f * C * C;
             float2* stg = staging + (warp - 8) * (32 * 16);
             const bool diag_tile = ti == tj;
+            if (a.store_mode == 3) {
+                float* diag = reinterpret_cast<float*>(staging + 8 * 32 * 16);     // [2][128] rsqrt of the diagonal
+                const int r0 = lane_grp * 32, r_loc = r0 + lane, cb = chalf * 64;
+                if (diag_tile) {
+                    float dv = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) if (cb + c == r_loc) dv = sr[c];
+                    asm volatile("bar.sync 1, 256;" ::: "memory");     // nobody still reads the previous diagonal
+                    if ((r_loc >> 6) == chalf) diag[ti * 128 + r_loc] = rsqrtf(dv);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+                const float ri = diag[ti * 128 + r_loc];
+                const float* __restrict__ dj = diag + tj * 128 + cb;
+                const int kind = a.out_kind;
+                const size_t row_dir = 0;
+                // Pointers walk with one add per element and the triangle tests are predicates on plain stores: the
+                // epilogue has ~16 us per tile before it holds up the MMAs, and only two warps per scheduler.
+                auto store_real = [&](auto diag_tag, auto kind_tag) {
+                    constexpr bool DG = decltype(diag_tag)::value;
+                    constexpr int KD = decltype(kind_tag)::value;
+                    float* __restrict__ outf = reinterpret_cast<float*>(a.coh_out) + (size_t)f * C * C;
+                    float* stgf = reinterpret_cast<float*>(stg);                 // [32][32] floats
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        if (DG && cb + c0 + 31 < r0) continue;                   // entirely below the diagonal
+                        float* pm = outf + (size_t)(tj * 128 + cb + c0) * C + ti * 128 + r_loc;   // mirrored (j, i)
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const int c = c0 + jj;
+                            const float w = ri * dj[c];
+                            const float zx = sr[c] * w;
+                            float zy = si[c] * w;
+                            if (DG && cb + c == r_loc) zy = 0.f;
+                            float val;
+                            if (KD == OUT_ABS) { const float q = zx * zx + zy * zy; val = q > 0.f ? q * rsqrtf(q) : 0.f; }
+                            else if (KD == OUT_POW) val = zx * zx + zy * zy;
+                            else val = convert_real(make_float2(zx, zy), kind);
+                            stgf[lane * 32 + (jj ^ lane)] = val;
+                            const float mv = (KD != OUT_ABS && KD != OUT_POW && (kind == OUT_IMAG || kind == OUT_ANGLE)) ? -val : val;
+                            if (!DG || cb + c > r_loc) *pm = mv;
+                            pm += C;
+                        }
+                        __syncwarp();
+                        float* pd = outf + (size_t)(ti * 128 + r0) * C + tj * 128 + cb + c0 + lane;   // direct (i, j)
+                        const int jcol = cb + c0 + lane;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const float v = stgf[r * 32 + (lane ^ r)];
+                            if (!DG || jcol >= r0 + r) *pd = v;
+                            pd += C;
+                        }
+                        __syncwarp();
+                    }
+                };
+                if (kind == OUT_FOURIER) {
+                    float2* __restrict__ outc = reinterpret_cast<float2*>(a.coh_out) + (size_t)f * C * C;
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                        if (diag_tile && cb + c0 + 15 < r0) continue;            // entirely below the diagonal
+                        float2* pm = outc + (size_t)(tj * 128 + cb + c0) * C + ti * 128 + r_loc;
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const int c = c0 + jj;
+                            const float w = ri * dj[c];
+                            float2 z = make_float2(sr[c] * w, si[c] * w);
+                            if (diag_tile && cb + c == r_loc) z.y = 0.f;
+                            stg[lane * 16 + (jj ^ (lane & 15))] = z;
+                            if (!diag_tile || cb + c > r_loc) *pm = make_float2(z.x, -z.y);
+                            pm += C;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int it = 0; it < 16; ++it) {
+                            const int r = 2 * it + (lane >> 4), cc = lane & 15;
+                            const float2 z = stg[r * 16 + (cc ^ (r & 15))];
+                            if (!diag_tile || cb + c0 + cc >= r0 + r)
+                                outc[(size_t)(ti * 128 + r0 + r) * C + tj * 128 + cb + c0 + cc] = z;
+                        }
+                        __syncwarp();
+                    }
+                } else if (kind == OUT_ABS) {
+                    if (diag_tile) store_real(std::true_type{}, std::integral_constant<int, OUT_ABS>{});
+                    else store_real(std::false_type{}, std::integral_constant<int, OUT_ABS>{});
+                } else if (kind == OUT_POW) {
+                    if (diag_tile) store_real(std::true_type{}, std::integral_constant<int, OUT_POW>{});
+                    else store_real(std::false_type{}, std::integral_constant<int, OUT_POW>{});
+                } else {
+                    if (diag_tile) store_real(std::true_type{}, std::integral_constant<int, -1>{});
+                    else store_real(std::false_type{}, std::integral_constant<int, -1>{});
+                }
+                (void)row_dir;
+                continue;
+            }
             if (a.store_mode == 2) {
                 int o = 0;
                 while (o + 1 < a.n_owners && f >= a.f_begin[o + 1]) ++o;
                 const int nf_o = a.f_begin[o + 1] - a.f_begin[o];
-                const int t = item % a.n_tiles;
                 float2* __restrict__ tile = a.owner_base[o] +
                     (((size_t)a.src_rank * nf_o + (size_t)(f - a.f_begin[o])) * a.n_tiles + t) * (128 * 128);
                 const int r0 = lane_grp * 32;                    // first tile row of this warp
@@ -641,7 +764,8 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     // cross terms as BF16 MMAs by default (1.1e-6 vs FP64, all-TF32: 1.3e-6); SPYB_TC_BF16=0 selects 3xTF32
     a.bf16_cross = 1;
     if (const char* e = getenv("SPYB_TC_BF16")) a.bf16_cross = atoi(e) != 0;
-    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2);
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2) +
+                        2 * 128 * sizeof(float);
 
     static bool configured = false;
     if (!configured) {
@@ -651,7 +775,7 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     int dev = 0, n_sm = 148;
     SPYB_CUDA(cudaGetDevice(&dev));
     SPYB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int n_items = d.n_freq * a.n_tiles;
+    const int n_items = a.store_mode == 3 ? d.n_freq : d.n_freq * a.n_tiles;
     const int grid = n_items < n_sm ? n_items : n_sm;
     csd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, a);
     SPYB_LAUNCH_CHECK("csd_tc_kernel");
@@ -665,6 +789,15 @@ int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream) {
     a.acc = reinterpret_cast<float2*>(d.acc);
     a.store_mode = 1;
     if (const char* e = getenv("SPYB_TC_STORE")) a.store_mode = atoi(e) != 0;
+    return launch_tc(d, a, stream);
+}
+
+int csd_coherence_tc(const CsdPlanarDesc& d, int out_kind, void* out, cudaStream_t stream) {
+    if (reinterpret_cast<uintptr_t>(out) % 16 != 0) return fail("tcgen05 CSD kernel needs 16-byte aligned buffers");
+    TcArgs a = {};
+    a.store_mode = 3;
+    a.coh_out = out;
+    a.out_kind = out_kind;
     return launch_tc(d, a, stream);
 }
 

@@ -52,6 +52,8 @@ bool csd_tc_supported(int n_chan, long long sx_f, long long sx_r);
 int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream);
 // "tile slots": the upper 128x128 tiles of every frequency go, unmirrored, to the rank owning the frequency
 // (peer-mapped base pointers; d.acc is ignored); csd_normalize_tiles sums the source ranks and normalises
+// contraction + coherency in one kernel (one rank, all rows at once; d.acc, d.alpha, d.beta are ignored)
+int csd_coherence_tc(const CsdPlanarDesc& d, int out_kind, void* out, cudaStream_t stream);
 int csd_tile_count(int n_chan);
 int csd_accumulate_tc_tiles(const CsdPlanarDesc& d, void* const* owner_base, const int* f_begin, int n_owners,
                             int src_rank, cudaStream_t stream);

@@ -211,6 +211,23 @@ class Engine:
             planes.data_ptr(), (planes.stride(0) if nF > 1 else 2 * R * Cn), 2 * Cn, R, nF, Cn,
             float(alpha), float(beta), ptrs, fb, n_own, int(src_rank), self.stream()))
 
+    def csd_coherence_planar(self, planes, output="abs", out=None):
+        """
+        planes [nF, R, 2, C] float32 with ALL (trial, taper) rows -> coherency [nF, C, C] in one kernel: tcgen05
+        contraction whose epilogue normalises, converts and mirrors (no cross-spectral matrix in memory).
+        """
+        assert planes.is_cuda and planes.dtype == torch.float32 and planes.dim() == 4 and planes.shape[2] == 2
+        nF, R, _, Cn = planes.shape
+        assert planes[0].is_contiguous()
+        kind = hm.out_kind(output)
+        if out is None:
+            out = torch.empty((nF, Cn, Cn), dtype=_CDTYPE[kind == 2], device=self.tdev)
+        assert out.is_contiguous() and out.numel() == nF * Cn * Cn and out.dtype == _CDTYPE[kind == 2]
+        _lib.check(self.lib.spyb_csd_coherence_planar(
+            planes.data_ptr(), (planes.stride(0) if nF > 1 else 2 * R * Cn), 2 * Cn, R, nF, Cn, kind,
+            out.data_ptr(), self.stream()))
+        return out
+
     def csd_normalize_tiles(self, slots, n_chan, output="abs", pre_scale=1.0, out=None):
         """slots [n_src, nF_loc, n_tiles, 128, 128] complex64 (local) -> coherency [nF_loc, C, C] of the summed slots."""
         assert slots.is_cuda and slots.dtype == torch.complex64 and slots.is_contiguous() and slots.dim() == 5

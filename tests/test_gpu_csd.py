@@ -247,3 +247,37 @@ def test_multi_gpu_tile_exchange_parity():
                           "--master-addr", "127.0.0.1", "--master-port", "29611", script],
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n_chan", [128, 256])
+@pytest.mark.parametrize("output", ["abs", "pow", "fourier", "real", "imag", "angle", "absreal", "absimag"])
+def test_fused_coherence_matches_two_kernel_path(engine, n_chan, output):
+    """contraction with normalising epilogue == accumulate_planar + normalize, every output conversion"""
+    import torch
+    planes, K = _planar_spectra(engine, 7, 256, n_chan, "dpss", {"NW": 2, "Kmax": 3}, seed=11)
+    want = engine.csd_normalize(engine.csd_accumulate_planar(planes, alpha=1.0 / K)[None], output=output,
+                                pre_scale=1.0 / 7)[0]
+    got = engine.csd_coherence_planar(planes, output=output)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if output == "angle":
+        assert nerr(torch.polar(torch.ones_like(got), got).cpu().numpy(),
+                    torch.polar(torch.ones_like(want), want).cpu().numpy()) <= 2e-5
+    else:
+        assert nerr(got.cpu().numpy(), want.cpu().numpy()) <= 3e-6
+    if output in ("abs", "pow", "real", "absreal", "absimag"):
+        assert torch.equal(got, got.transpose(1, 2))
+    if output == "fourier":
+        assert (got - got.conj().transpose(1, 2)).abs().max().item() == 0.0
+    if output in ("imag", "angle"):
+        assert (got + got.transpose(1, 2)).abs().max().item() == 0.0
+
+
+def test_fused_coherence_many_frequencies(engine):
+    """more frequencies than SMs (several per CTA, uneven split) and a row count that is not a multiple of 16"""
+    import torch
+    torch.manual_seed(3)
+    nF, R, C = 333, 37, 256
+    planes = torch.randn((nF, R, 2, C), device=engine.tdev)
+    want = engine.csd_normalize(engine.csd_accumulate_planar(planes)[None], output="abs", pre_scale=1.0 / R)[0]
+    got = engine.csd_coherence_planar(planes, output="abs")
+    assert nerr(got.cpu().numpy(), want.cpu().numpy()) <= 3e-6

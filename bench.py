@@ -168,7 +168,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     return 0
 
 
@@ -473,10 +473,29 @@ def run_gpu_arm(args):
             "roofline": roofline, "kernels": kernels, "hbm_pipeline": hbm_pipeline,
             "cpu_baseline": cpu_info, "clocks": clocks,
         }
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything libraries print to stdout (NCCL's version banner, ...) goes to stderr; the JSON line alone is
+    written to the real stdout by `_emit`."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
@@ -491,6 +510,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
+        _quiet_stdout()
         return run_reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
@@ -499,6 +519,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000),
                os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    _quiet_stdout()
     return run_gpu_arm(args)
 
 

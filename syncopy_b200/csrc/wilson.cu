@@ -1174,7 +1174,8 @@ int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double r
         { zd* t = psi0; psi0 = psi0_next; psi0_next = t; }
         // err = max |CSD - psi psi^H| / |CSD|                 (wilson_sf.py:104-106)
         SPYB_CUDA(cudaMemsetAsync(w.err_bits, 0, sizeof(unsigned long long), st));
-        if (run_gemm<1, 1>(psi, n2, psi, n2, nullptr, 0, S, n2, w.err_bits, n, nf, false, st)) return 1;
+        // S and psi psi^H are Hermitian: the upper tiles carry every value of |S - psi psi^H| / |S|
+        if (run_gemm<1, 1>(psi, n2, psi, n2, nullptr, 0, S, n2, w.err_bits, n, nf, true, st)) return 1;
         unsigned long long bits = 0;
         SPYB_CUDA(cudaMemcpyAsync(&bits, w.err_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
         SPYB_CUDA(cudaStreamSynchronize(st));

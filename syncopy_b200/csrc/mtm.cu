@@ -313,12 +313,7 @@ static int launch_log2(int log2n, const MtmArgs& a, cudaStream_t st) {
         case 9:  return launch_one<9, 4, BLUE>(a, st);
         case 10: return launch_one<10, 4, BLUE>(a, st);
         case 11: return launch_one<11, 4, BLUE>(a, st);
-        case 12: {
-            static const int p12 = getenv("SPYB_MTM_P12") ? atoi(getenv("SPYB_MTM_P12")) : 4;
-            if (p12 == 1) return launch_one<12, 1, BLUE>(a, st);
-            if (p12 == 2) return launch_one<12, 2, BLUE>(a, st);
-            return launch_one<12, 4, BLUE>(a, st);
-        }
+        case 12: return launch_one<12, 2, BLUE>(a, st);     // 512 threads: room for ~100 registers, no spills
         case 13: return launch_one<13, 2, BLUE>(a, st);
         case 14: return launch_one<14, 1, BLUE>(a, st);
         default: return fail("unsupported block FFT size 2^%d", log2n);

@@ -195,7 +195,7 @@ def spectral_dyadic_product_cF(specs, send_idx=None, send_N=None, rec_idx=None, 
     eng = get_engine()
     x = eng.to_device(np.ascontiguousarray(specs, dtype=np.complex64), dtype=torch.complex64)
     # [T, K, F, C] -> one "frequency" per (time, freq) pair with K rows each
-    x = x.permute(0, 2, 1, 3).reshape(n_time * n_freq, n_taper, n_chan)
+    x = x.permute(0, 2, 1, 3).reshape(n_time * n_freq, n_taper, n_chan).contiguous()   # (a view when n_time == 1)
     if send_idx is not None:
         cs = eng.csd_accumulate(x, alpha=1.0 / n_taper, idx_i=np.asarray(send_idx), idx_j=np.asarray(rec_idx))
     else:

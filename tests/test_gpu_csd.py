@@ -281,3 +281,24 @@ def test_fused_coherence_many_frequencies(engine):
     want = engine.csd_normalize(engine.csd_accumulate_planar(planes)[None], output="abs", pre_scale=1.0 / R)[0]
     got = engine.csd_coherence_planar(planes, output="abs")
     assert nerr(got.cpu().numpy(), want.cpu().numpy()) <= 3e-6
+
+
+def test_analog_route_equals_spectral_route(engine):
+    """tests/test_connectivity.py:434-473: coherence from AnalogData (cross_spectra_cF) equals the route over
+    complex spectra (mtmfft_cF output='fourier' -> spectral_dyadic_product_cF), trial average and normalisation
+    included."""
+    from syncopy_b200 import compute_functions as cf
+    trials = synth.white_noise(6, 400, 10)
+    fs = 400.
+    foi = np.fft.rfftfreq(400, 1 / fs)
+    mk = dict(samplerate=fs, nSamples=None, taper="dpss", taper_opt={"NW": 2, "Kmax": 3})
+    a = [cf.cross_spectra_cF(t.copy(), fs, taper="dpss", taper_opt={"NW": 2, "Kmax": 3}, polyremoval=0)[0]
+         for t in trials]
+    b = []
+    for t in trials:
+        spec, _ = cf.mtmfft_cF(t.copy(), foi=foi, polyremoval=0, output="fourier", keeptapers=True, method_kwargs=mk)
+        b.append(cf.spectral_dyadic_product_cF(spec))
+    coh_a = cf.normalize_csd_cF(oc.trial_average(a), "abs")
+    coh_b = cf.normalize_csd_cF(oc.trial_average(b), "abs")
+    assert coh_a.shape == coh_b.shape == (1, 201, 10, 10)
+    assert nerr(coh_a, coh_b) <= 1e-5

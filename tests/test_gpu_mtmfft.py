@@ -135,3 +135,26 @@ def test_full_size_parseval(engine):
     energy_f = (spec * w[:, None]).sum(dim=0) / 4096
     energy_t = (xd[0].double() ** 2).sum(dim=0)
     assert torch.allclose(energy_f, energy_t, rtol=1e-5)
+
+
+def test_cfg1_reference_frontend_setup(engine):
+    """BASELINE cfg-1 = the reference's TestMTMFFT data (tests/test_specest.py:99-150): 8 trials x 32 channels of
+    1 s sines (amplitude pi, one frequency per channel) at fs = 1024; every channel peaks at its own frequency
+    (:229-233) and the GPU spectrum matches the oracle."""
+    from syncopy_b200 import batched
+    from oracle import spectral as osp
+    fs, n, n_chan, n_trials = 1024, 1024, 32, 8
+    rng = np.random.default_rng(42)
+    freqs = rng.choice(np.arange(4, 500), size=n_chan, replace=False)
+    t = np.arange(n) / fs
+    trials = np.stack([np.stack([np.pi * np.sin(2 * np.pi * f * t + rng.uniform(0, 2 * np.pi)) for f in freqs], axis=1)
+                       for _ in range(n_trials)]).astype("f4")
+    spec, f_axis = batched.mtmfft(trials, fs, taper="hann", polyremoval=0, output="pow", keeptapers=False,
+                                  to_host=True)
+    assert spec.shape == (n_trials, 1, n // 2 + 1, n_chan)
+    for k in range(n_trials):
+        assert np.array_equal(f_axis[spec[k, 0].argmax(axis=0)], freqs.astype(float))
+    mk = dict(samplerate=fs, nSamples=None, taper="hann", taper_opt={})
+    want, _ = osp.mtmfft_cF(trials[3].copy(), foi=f_axis, polyremoval=0, output="pow", keeptapers=False,
+                            method_kwargs=mk)
+    assert nerr(spec[3:4], want) <= 1e-5

@@ -94,3 +94,21 @@ def test_superlet_cf_vs_oracle(engine, adaptive):
     # the 30 Hz packet shows up at the right place: power at 30 Hz after 0.5 s >> before
     k30 = 2
     assert got[int(0.8 * fs):, 0, k30, 0].mean() > 20 * got[:int(0.3 * fs), 0, k30, 0].mean()
+
+
+def test_cfg5_shape_subset_vs_oracle(engine):
+    """BASELINE cfg-5 shape (8192 samples x 64 channels, Morlet w0 = 6, fs = 1000), a subset of the 50 scales so that
+    the CPU oracle finishes in seconds; includes the lowest frequency, whose kernel support (9681 taps) exceeds the trial."""
+    from syncopy_b200 import batched
+    from syncopy_b200 import hostmath as hm
+    fs = 1000.
+    x = synth.white_noise(2, 8192, 64)
+    wav_o, wav_g = otf.Morlet(6), hm.Morlet(6)
+    foi = np.array([1., 9., 41., 99.])
+    scales = wav_o.scale_from_period(1 / foi)
+    got = batched.wavelet(x, fs, scales, wav_g, polyremoval=0, output="pow", to_host=True)
+    assert got.shape == (2, 8192, 1, 4, 64)
+    for k in range(2):
+        want = otf.wavelet_cF(x[k].copy(), slice(None), slice(None), toi=None, polyremoval=0, output="pow",
+                              method_kwargs=dict(samplerate=fs, scales=scales, wavelet=wav_o))
+        assert nerr(got[k], want) <= 2 * TOL

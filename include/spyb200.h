@@ -175,9 +175,16 @@ int spyb_detrend(const float* x, int n_trials, long long trial_stride, int n_sam
  *   expo    float32 [n_scales][max_fac] exponents (principal-branch complex power; 1 = none)
  *   n_fac   int32 [n_scales] number of factors in use
  *   out     [n_trials][n_time][n_scales][n_chan] float32 or complex64 by out_kind; rows n = 0 .. n_time-1
+ *   transposed  1: xspec is [n_trials][n_chan][n_dft/2+1] and out is [n_trials][n_scales][n_chan][n_time], the
+ *           layouts in which every global access of the kernel is contiguous across a warp (a block owns one
+ *           channel of one scale); spyb_transpose converts to / from the reference layouts at HBM speed
  */
 int spyb_cwt(const void* xspec, int n_trials, int n_chan, int n_dft, const void* kern, const float* expo,
-             const int* n_fac, int n_scales, int max_fac, int n_time, int out_kind, void* out, void* stream);
+             const int* n_fac, int n_scales, int max_fac, int n_time, int out_kind, int transposed, void* out,
+             void* stream);
+
+/* batched 2-D transpose of 4- or 8-byte elements: in [batch][rows][cols] -> out [batch][cols][rows] */
+int spyb_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, void* stream);
 
 /* dst[t][i][:] = src[t][idx[i]][:], rows of row_elems float32 (time post-selection, compRoutines.py:593) */
 int spyb_gather_rows(const float* src, int n_trials, long long src_trial_stride, const int* idx, int n_idx,

@@ -45,7 +45,8 @@ PROTOTYPES = {
     "spyb_peer_free": (_i, [_vp]),
     "spyb_csd_normalize": (_i, [_vp, _ll, _i, _f, _i, _vp, _vp]),
     "spyb_detrend": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _ll, _vp]),
-    "spyb_cwt": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "spyb_cwt": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "spyb_transpose": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "spyb_gather_rows": (_i, [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp]),
     "spyb_scale": (_i, [_vp, _ll, _f, _vp]),
     "spyb_regularize_workspace_bytes": (_ll, [_i, _i]),

@@ -182,10 +182,16 @@ int spyb_detrend(const float* x, int n_trials, long long trial_stride, int n_sam
                    static_cast<cudaStream_t>(stream));
 }
 
+int spyb_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, void* stream) {
+    return transpose2d(in, out, batch, rows, cols, elem_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int spyb_cwt(const void* xspec, int n_trials, int n_chan, int n_dft, const void* kern, const float* expo,
-             const int* n_fac, int n_scales, int max_fac, int n_time, int out_kind, void* out, void* stream) {
+             const int* n_fac, int n_scales, int max_fac, int n_time, int out_kind, int transposed, void* out,
+             void* stream) {
     if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
     CwtDesc d;
+    d.transposed = transposed ? 1 : 0;
     d.xspec = xspec; d.n_trials = n_trials; d.n_chan = n_chan; d.n_dft = n_dft;
     d.kern = kern; d.expo = expo; d.n_fac = n_fac; d.n_scales = n_scales; d.max_fac = max_fac;
     d.n_time = n_time; d.out_kind = out_kind; d.out = out;

@@ -86,6 +86,8 @@ struct CwtArgs {
     int n_time;                // rows written: n = 0 .. n_time-1
     int out_kind;
     void* out;                 // [trial][n_time][scale][chan]
+    int transposed;            // 1: xspec is [trial][chan][L/2+1] and out is [trial][scale][chan][n_time] -- every
+                               // global access of the kernel is then contiguous across the threads of a warp
     const float2* tw;
 };
 
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(MAXT, 1) cwt_kernel(const CwtArgs a) {
     const int nf = a.n_fac[sc];
     const int half = N / 2;
     const float2* __restrict__ X = a.xspec + (long long)trial * (half + 1) * a.n_chan;
+    const long long xs = a.transposed ? 1 : a.n_chan;                               // stride between bins
+    const long long xc = a.transposed ? (long long)c * (half + 1) : (long long)c;   // offset of the channel
 
     float2 v[16];
     for (int fj = 0; fj < nf; ++fj) {
@@ -127,8 +131,8 @@ __global__ void __launch_bounds__(MAXT, 1) cwt_kernel(const CwtArgs a) {
             const int k = j + NT * e;
             float2 xv = make_float2(0.f, 0.f);
             if (c_ok) {
-                if (k <= half) xv = __ldg(X + (long long)k * a.n_chan + c);
-                else { xv = __ldg(X + (long long)(N - k) * a.n_chan + c); xv.y = -xv.y; }
+                if (k <= half) xv = __ldg(X + (long long)k * xs + xc);
+                else { xv = __ldg(X + (long long)(N - k) * xs + xc); xv.y = -xv.y; }
             }
             v[e] = cconj(cmul(xv, __ldg(T + k)));
         }
@@ -145,8 +149,10 @@ __global__ void __launch_bounds__(MAXT, 1) cwt_kernel(const CwtArgs a) {
 
     // ---- output: element (n, scale, chan) of this trial ----
     if (!c_ok) return;
-    const long long row = (long long)a.n_scales * a.n_chan;
-    const long long base = (long long)trial * a.n_time * row + (long long)sc * a.n_chan + c;
+    const long long row = a.transposed ? 1 : (long long)a.n_scales * a.n_chan;
+    const long long base = a.transposed
+        ? (((long long)trial * a.n_scales + sc) * a.n_chan + c) * a.n_time
+        : (long long)trial * a.n_time * a.n_scales * a.n_chan + (long long)sc * a.n_chan + c;
     for (int n = j; n < a.n_time; n += NT) {
         float2 z;
         if (nf > 1) z = zacc[n * P + p];
@@ -195,6 +201,7 @@ int cwt_factors(const CwtDesc& d, cudaStream_t stream) {
     a.expo = d.expo; a.n_fac = d.n_fac;
     a.n_scales = d.n_scales; a.max_fac = d.max_fac;
     a.n_time = d.n_time; a.out_kind = d.out_kind; a.out = d.out;
+    a.transposed = d.transposed;
     a.tw = pl->tw;
     const bool acc = d.max_fac > 1;
     switch (pl->log2n) {
@@ -211,6 +218,46 @@ int cwt_factors(const CwtDesc& d, cudaStream_t stream) {
         case 14: return launch_cwt<14, 1>(a, acc, stream);
         default: return fail("cwt: transform length 2^%d not supported (max 2^14)", pl->log2n);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// batched 2-D transpose of 4- or 8-byte elements: in [b][rows][cols] -> out [b][cols][rows] (32 x 32 tiles through
+// padded shared memory, both sides coalesced); brings spectra / results into and out of the layouts above
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int rows, int cols) {
+    __shared__ T tile[32][33];
+    const long long b = blockIdx.z;
+    const T* __restrict__ ib = in + b * rows * cols;
+    T* __restrict__ ob = out + b * rows * cols;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + 8 * i][tx] = ib[(long long)r * cols + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (r < rows && c < cols) ob[(long long)c * rows + r] = tile[tx][ty + 8 * i];
+    }
+}
+
+int transpose2d(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t stream) {
+    if (batch <= 0 || rows <= 0 || cols <= 0) return 0;
+    if (elem_bytes != 4 && elem_bytes != 8) return fail("transpose: element size must be 4 or 8 bytes (got %d)", elem_bytes);
+    const unsigned gy = (unsigned)((rows + 31) / 32);
+    if (batch > 65535 || gy > 65535) return fail("transpose: too many batches / rows per launch");
+    dim3 grid((cols + 31) / 32, gy, batch);
+    if (elem_bytes == 4)
+        transpose_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), static_cast<float*>(out), rows, cols);
+    else
+        transpose_kernel<float2><<<grid, 256, 0, stream>>>(static_cast<const float2*>(in), static_cast<float2*>(out), rows, cols);
+    SPYB_LAUNCH_CHECK("transpose_kernel");
+    count_launch();
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -61,6 +61,7 @@ int csd_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, fl
                         void* out, cudaStream_t stream);
 // Wavelet / superlet transforms as FFT convolutions (cwt.cu)
 struct CwtDesc {
+    int transposed = 0;              // 1: xspec [trial][chan][L/2+1], out [trial][scale][chan][n_time]
     const void* xspec = nullptr;     // device complex64 [trial][L/2+1][chan], spectra of the zero-padded trials
     int n_trials = 0, n_chan = 0, n_dft = 0;
     const void* kern = nullptr;      // device complex64 [scale][max_fac][L] = FFT_L(h) / L
@@ -71,6 +72,7 @@ struct CwtDesc {
     void* out = nullptr;             // device [trial][n_time][scale][chan]
 };
 int cwt_factors(const CwtDesc& d, cudaStream_t stream);
+int transpose2d(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t stream);
 int detrend(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, int polyremoval,
             float* out, long long out_trial_stride, cudaStream_t stream);
 int gather_rows(const float* src, int n_trials, long long src_trial_stride, const int* idx, int n_idx,

@@ -306,9 +306,17 @@ class Engine:
         if out is None:
             out = torch.empty((B, N, nS, Cn), dtype=dt, device=self.tdev)
         assert out.is_contiguous() and out.dtype == dt and tuple(out.shape) == (B, N, nS, Cn)
-        _lib.check(self.lib.spyb_cwt(xspec.data_ptr(), B, Cn, L, plan["kern"].data_ptr(), plan["expo"].data_ptr(),
-                                     plan["nfac"].data_ptr(), nS, plan["max_fac"], N, kind, out.data_ptr(),
+        # the transform kernel owns one channel of one scale per block: feed it channel-major spectra and let it
+        # write time-contiguous rows, then transpose into the reference layout [time][scale][channel]
+        nF = L // 2 + 1
+        xs_t = self.scratch("cwt_xspec_t", (B, Cn, nF), torch.complex64)
+        _lib.check(self.lib.spyb_transpose(xspec.data_ptr(), xs_t.data_ptr(), B, nF, Cn, 8, self.stream()))
+        out_t = self.scratch("cwt_out_t" + ("c" if kind == 2 else "f"), (B, nS * Cn, N), dt)
+        _lib.check(self.lib.spyb_cwt(xs_t.data_ptr(), B, Cn, L, plan["kern"].data_ptr(), plan["expo"].data_ptr(),
+                                     plan["nfac"].data_ptr(), nS, plan["max_fac"], N, kind, 1, out_t.data_ptr(),
                                      self.stream()))
+        _lib.check(self.lib.spyb_transpose(out_t.data_ptr(), out.data_ptr(), B, nS * Cn, N, 8 if kind == 2 else 4,
+                                           self.stream()))
         return out
 
     def gather_rows(self, src, idx):

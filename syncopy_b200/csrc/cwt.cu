@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(MAXT, 1) cwt_kernel(const CwtArgs a) {
     const long long xs = a.transposed ? 1 : a.n_chan;                               // stride between bins
     const long long xc = a.transposed ? (long long)c * (half + 1) : (long long)c;   // offset of the channel
 
+    // superlets with a magnitude output only need |z|: the geometric mean runs on log-magnitudes
+    const bool mag_only = nf > 1 && (a.out_kind == OUT_POW || a.out_kind == OUT_ABS);
     float2 v[16];
     for (int fj = 0; fj < nf; ++fj) {
         const float2* __restrict__ T = a.kern + ((long long)sc * a.max_fac + fj) * N;
@@ -138,10 +140,19 @@ __global__ void __launch_bounds__(MAXT, 1) cwt_kernel(const CwtArgs a) {
         }
         block_fft<LOG2N, P>(v, s, a.tw, j, p);          // natural order result in s (ends with a barrier)
         if (nf > 1) {
-            for (int n = j; n < a.n_time; n += NT) {
-                float2 y = cconj(s[fft_pad(n) * P + p]);
-                if (ex != 1.f) y = cpow_real(y, ex);
-                zacc[n * P + p] = fj == 0 ? y : cmul(zacc[n * P + p], y);
+            if (mag_only) {
+                // |prod_j y_j^a_j| = exp2(sum_j a_j log2|y_j|): no phases, no complex powers (pow / abs outputs)
+                for (int n = j; n < a.n_time; n += NT) {
+                    const float2 y = s[fft_pad(n) * P + p];
+                    const float l = 0.5f * ex * __log2f(y.x * y.x + y.y * y.y);
+                    zacc[n * P + p].x = fj == 0 ? l : zacc[n * P + p].x + l;
+                }
+            } else {
+                for (int n = j; n < a.n_time; n += NT) {
+                    float2 y = cconj(s[fft_pad(n) * P + p]);
+                    if (ex != 1.f) y = cpow_real(y, ex);
+                    zacc[n * P + p] = fj == 0 ? y : cmul(zacc[n * P + p], y);
+                }
             }
             __syncthreads();                             // exchange buffer is rewritten by the next factor
         }
@@ -155,6 +166,11 @@ __global__ void __launch_bounds__(MAXT, 1) cwt_kernel(const CwtArgs a) {
         : (long long)trial * a.n_time * a.n_scales * a.n_chan + (long long)sc * a.n_chan + c;
     for (int n = j; n < a.n_time; n += NT) {
         float2 z;
+        if (mag_only) {
+            const float mag = exp2f(zacc[n * P + p].x);
+            reinterpret_cast<float*>(a.out)[base + (long long)n * row] = a.out_kind == OUT_POW ? mag * mag : mag;
+            continue;
+        }
         if (nf > 1) z = zacc[n * P + p];
         else {
             z = cconj(s[fft_pad(n) * P + p]);

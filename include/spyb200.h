@@ -228,6 +228,23 @@ int spyb_wilson(const void* csd, int n_freq, int n_chan, int n_iter, double rtol
 int spyb_granger(const void* csd, const void* H, const double* Sigma, int n_freq, int n_chan, float* out,
                  void* stream);
 
+/*
+ * spyb_wilson over several ranks that all hold the same (all-reduced) csd: everything in an iteration except the
+ * plus operator (wilson_sf.py:154-184) is independent per frequency, so rank r only factorises its slab
+ * [f_lo, f_hi); the plus operator needs every frequency of every matrix element and is replicated.  The library
+ * calls `exchange` twice per iteration, in stream order:
+ *   what = 0: buf = lag-domain work array, n_rows = 2(n_freq-1) rows of row_bytes bytes; the rank has written rows
+ *             [f_lo, f_hi) and the mirror rows 2(n_freq-1) - f for f in [max(f_lo,1), min(f_hi, n_freq-1));
+ *             the callback must bring in the rows of all other ranks (e.g. one NCCL broadcast per rank and range);
+ *   what = 1: buf = one float64, replace it by its maximum over the ranks.
+ * A non-zero return of the callback aborts.  H is written for the slab only; Sigma, converged, err, iterations are
+ * identical on every rank.  `exchange_ctx` is passed through.
+ */
+typedef int (*spyb_exchange_fn)(void* ctx, int what, void* buf, long long row_bytes, int n_rows);
+int spyb_wilson_sharded(const void* csd, int n_freq, int n_chan, int n_iter, double rtol, void* H, double* Sigma,
+                        int* converged_host, double* err_host, int* iters_host, void* work, long long work_bytes,
+                        int f_lo, int f_hi, spyb_exchange_fn exchange, void* exchange_ctx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

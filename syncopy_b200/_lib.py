@@ -20,6 +20,8 @@ _lib = None
 
 _vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+# int exchange(void* ctx, int what, void* buf, long long row_bytes, int n_rows)  -- spyb_wilson_sharded
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int)
 
 # name -> (restype, argtypes); must list every symbol of include/spyb200.h
 PROTOTYPES = {
@@ -54,6 +56,7 @@ PROTOTYPES = {
     "spyb_wilson_workspace_bytes": (_ll, [_i, _i]),
     "spyb_wilson": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _ip, _dp, _ip, _vp, _ll, _vp]),
     "spyb_granger": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "spyb_wilson_sharded": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _ip, _dp, _ip, _vp, _ll, _i, _i, EXCHANGE_FN, _vp, _vp]),
 }
 
 

@@ -275,6 +275,10 @@ def _coherence_tiles(eng, trials, samplerate, nSamples, foi, taper, taper_opt, p
     return _finish(res, to_host, out_host), freqs
 
 
+def n_chan_of(csd):
+    return int(csd.shape[-1])
+
+
 def granger(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_opt=None, polyremoval=0,
             rtol=5e-6, nIter=100, cond_max=1e4, to_host=False, engine=None, impl=0, reduce_group=None):
     """
@@ -292,8 +296,29 @@ def granger(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_o
         n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group)
     csd_av = eng.scale_(res.csd_sum, 1.0 / n_total)
     reg, factor, ini_cn = eng.regularize_csd(csd_av, cond_max=cond_max, eps_max=1e-1)
-    H, Sigma, conv, err, iters = eng.wilson_sf(reg, n_iter=nIter, rtol=rtol)
-    G = eng.granger(reg, H, Sigma)[None]
+    world = 1
+    if reduce_group is not None:
+        import torch.distributed as dist
+        world = dist.get_world_size(reduce_group)
+    if world > 1 and not os.environ.get("SPYB_WILSON_REPLICATED"):
+        # every rank holds the same averaged CSD: factorise one frequency slab per rank (the plus operator is
+        # replicated, its inputs are exchanged by broadcasts), then gather the Granger slabs
+        import torch.distributed as dist
+        from .distributed import WilsonExchange
+        wx = WilsonExchange(eng, reg.shape[0], reduce_group)
+        H, Sigma, conv, err, iters = eng.wilson_sf(reg, n_iter=nIter, rtol=rtol, slab=wx.slab, exchange=wx)
+        lo, hi = wx.slab
+        G = torch.zeros((reg.shape[0], n_chan_of(reg), n_chan_of(reg)), dtype=torch.float32, device=eng.tdev)
+        if hi > lo:
+            G[lo:hi] = eng.granger(reg[lo:hi].contiguous(), H[lo:hi].contiguous(), Sigma)
+        for r in range(world):
+            a, b = wx.f_begin[r], wx.f_begin[r + 1]
+            if b > a:
+                dist.broadcast(G[a:b], src=dist.get_global_rank(reduce_group, r), group=reduce_group)
+        G = G[None]
+    else:
+        H, Sigma, conv, err, iters = eng.wilson_sf(reg, n_iter=nIter, rtol=rtol)
+        G = eng.granger(reg, H, Sigma)[None]
     meta = {"converged--bool": np.array(conv), "max rel. err--float": np.array(err),
             "reg. factor--float": np.array(factor), "initial cond. num--float": np.array(np.float32(ini_cn)),
             "iterations": iters}

@@ -226,7 +226,16 @@ int spyb_wilson(const void* csd, int n_freq, int n_chan, int n_iter, double rtol
                 void* stream) {
     if (!converged_host || !err_host) return fail("converged_host / err_host must not be NULL");
     return wilson_sf(csd, n_freq, n_chan, n_iter, rtol, H, Sigma, converged_host, err_host, iters_host, work,
-                     work_bytes, static_cast<cudaStream_t>(stream));
+                     work_bytes, 0, n_freq, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_wilson_sharded(const void* csd, int n_freq, int n_chan, int n_iter, double rtol, void* H, double* Sigma,
+                        int* converged_host, double* err_host, int* iters_host, void* work, long long work_bytes,
+                        int f_lo, int f_hi, spyb_exchange_fn exchange, void* exchange_ctx, void* stream) {
+    if (!converged_host || !err_host) return fail("converged_host / err_host must not be NULL");
+    if (!exchange) return fail("spyb_wilson_sharded needs an exchange callback (use spyb_wilson on one rank)");
+    return wilson_sf(csd, n_freq, n_chan, n_iter, rtol, H, Sigma, converged_host, err_host, iters_host, work,
+                     work_bytes, f_lo, f_hi, exchange, exchange_ctx, static_cast<cudaStream_t>(stream));
 }
 
 int spyb_granger(const void* csd, const void* H, const double* Sigma, int n_freq, int n_chan, float* out,

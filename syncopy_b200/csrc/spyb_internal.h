@@ -88,9 +88,10 @@ int regularize_csd(const void* csd_c64, int n_freq, int n_chan, double cond_max,
                    void* out_c128, double* eps_host, double* cond0_host, void* work, long long work_bytes,
                    cudaStream_t stream);
 long long wilson_workspace_bytes(int n_freq, int n_chan);
+typedef int (*WilsonExchangeFn)(void* ctx, int what, void* buf, long long row_bytes, int n_rows);
 int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double rtol, void* H_out, double* Sigma_out,
               int* converged_host, double* err_host, int* iters_host, void* work, long long work_bytes,
-              cudaStream_t stream);
+              int f_lo, int f_hi, WilsonExchangeFn exchange, void* exchange_ctx, cudaStream_t stream);
 int granger(const void* csd_c128, const void* H, const double* Sigma, int n_freq, int n_chan, float* out,
             cudaStream_t stream);
 

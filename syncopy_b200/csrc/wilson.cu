@@ -564,10 +564,10 @@ __global__ void pair_table_kernel(int2* tab, int n) {
 // conjugated; only its real part is used afterwards)
 __global__ void __launch_bounds__(128) plus_pack_kernel(const zd* __restrict__ g, int nf, int n,
                                                         const int2* __restrict__ tab, long long E,
-                                                        zd* __restrict__ W) {
+                                                        zd* __restrict__ W, int row0) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const int f = blockIdx.y;                 // 0 .. len-1
+    const int f = row0 + blockIdx.y;          // row of the full circle, 0 .. len-1
     const int len = 2 * (nf - 1);
     const int2 ij = tab[e];
     const int fs = f < nf ? f : len - f;
@@ -613,10 +613,11 @@ __global__ void __launch_bounds__(128) plus_causal_kernel(const zd* __restrict__
 // M[f] = gplus[f] + S for the one-sided frequencies (wilson_sf.py:101)
 __global__ void __launch_bounds__(128) plus_unpack_kernel(const zd* __restrict__ Zf, int nf, int n,
                                                           const int2* __restrict__ tab, long long E,
-                                                          const double* __restrict__ g0, zd* __restrict__ M) {
+                                                          const double* __restrict__ g0, zd* __restrict__ M,
+                                                          int row0) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const int f = blockIdx.y;                 // 0 .. nf-1
+    const int f = row0 + blockIdx.y;          // 0 .. nf-1
     const int len = 2 * (nf - 1);
     const int2 ij = tab[e];
     const zd z1 = Zf[(long long)f * E + e];
@@ -650,13 +651,14 @@ __global__ void gamma0_kernel(const zd* __restrict__ S, int nf, int n, zd* __res
 }
 
 // psi[f] = L0^T for every f, psi0 = L0^T (wilson_sf.py:66-67,151)
-__global__ void psi_init_kernel(const zd* __restrict__ L0, int n, zd* __restrict__ psi0, zd* __restrict__ psi) {
+__global__ void psi_init_kernel(const zd* __restrict__ L0, int n, zd* __restrict__ psi0, zd* __restrict__ psi,
+                                int f0) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * n) return;
     const int i = idx / n, j = idx - i * n;
     const zd v = L0[(long long)j * n + i];
     if (blockIdx.y == 0) psi0[idx] = v;
-    psi[(long long)blockIdx.y * n * n + idx] = v;
+    psi[(long long)(f0 + blockIdx.y) * n * n + idx] = v;
 }
 
 __global__ void eye_kernel(zd* I, int n) {
@@ -1106,14 +1108,21 @@ int regularize_csd(const void* csd_c64, int n_freq, int n_chan, double cond_max,
     return 0;
 }
 
+// Frequency-slab sharding: everything in an iteration except the plus operator is independent per frequency, so a
+// rank only factorises its slab [f_lo, f_hi).  The plus operator needs every frequency of every matrix element; it is
+// replicated: each rank packs its rows of the lag-domain work array, `exchange(ctx, 0, ...)` lets the caller gather
+// the rows of all ranks (stream-ordered, e.g. NCCL broadcasts), and `exchange(ctx, 1, ...)` max-reduces the error
+// scalar.  With exchange == NULL (one rank) the slab is the whole axis.  H_out is written for the slab only.
 int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double rtol, void* H_out, double* Sigma_out,
               int* converged_host, double* err_host, int* iters_host, void* work, long long work_bytes,
-              cudaStream_t st) {
+              int f_lo, int f_hi, WilsonExchangeFn exchange, void* exchange_ctx, cudaStream_t st) {
     const int nf = n_freq, n = n_chan;
     if (nf < 2) return fail("wilson_sf needs at least two frequencies");
     if (n < 1 || n > MAX_CHAN) return fail("wilson_sf supports 1..%d channels (got %d)", MAX_CHAN, n);
     if (work_bytes < wilson_workspace_bytes(nf, n))
         return fail("wilson_sf: workspace too small (%lld < %lld bytes)", work_bytes, wilson_workspace_bytes(nf, n));
+    if (exchange == nullptr) { f_lo = 0; f_hi = nf; }
+    if (f_lo < 0 || f_hi > nf || f_lo > f_hi) return fail("wilson_sf: bad frequency slab [%d, %d) of %d", f_lo, f_hi, nf);
     if (ensure_fact_smem()) return 1;
     WilsonBuffers w = carve_wilson(work, nf, n);
     const zd* S = static_cast<const zd*>(csd_c128);
@@ -1123,6 +1132,11 @@ int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double r
     const FftPlanZ plan = plan_fft(len);
     const unsigned eb = (unsigned)((E + 127) / 128);
     const unsigned nb2 = (unsigned)((n2 + 255) / 256);
+    const int nfl = f_hi - f_lo;                      // frequencies of this rank
+    const long long so = (long long)f_lo * n2;        // element offset of the slab in every [nF][C][C] stack
+    // rows of the full circle this rank packs: its slab and the mirror image of the slab's interior
+    const int m_lo = f_lo > 1 ? f_lo : 1, m_hi = f_hi < nf - 1 ? f_hi : nf - 1;    // mirrored rows: len - f, f in [m_lo, m_hi)
+    const int mrow0 = len - m_hi + 1, mrows = m_hi > m_lo ? m_hi - m_lo : 0;
 
     SPYB_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int) * ((size_t)nf + 8), st));
     twiddle_kernel<<<(len + 255) / 256, 256, 0, st>>>(w.tw, len);
@@ -1132,14 +1146,14 @@ int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double r
     eye_kernel<<<nb2, 256, 0, st>>>(w.eye, n);
     SPYB_LAUNCH_CHECK("eye_kernel"); count_launch();
 
-    // psi0 = chol(Re sym gamma_0)^T, psi = tile(psi0)     (wilson_sf.py:66-67,123-151)
+    // psi0 = chol(Re sym gamma_0)^T, psi = tile(psi0)     (wilson_sf.py:66-67,123-151); gamma_0 needs every frequency
     gamma0_kernel<<<nb2, 256, 0, st>>>(S, nf, n, w.G0);
     SPYB_LAUNCH_CHECK("gamma0_kernel"); count_launch();
     if (run_potrf(w.G0, 0, w.L0, 0, n, 1, w.info + nf, st)) return 1;
     // U = chol(CSD)                                         (wilson_sf.py:76)
-    if (run_potrf(S, n2, w.Lchol, n2, n, nf, w.info, st)) return 1;
+    if (nfl > 0 && run_potrf(S + so, n2, w.Lchol + so, n2, n, nfl, w.info + f_lo, st)) return 1;
     if (check_info(w.info, nf + 1, "wilson_sf (Cholesky of the CSD)", st)) return 1;
-    psi_init_kernel<<<dim3(nb2, nf), 256, 0, st>>>(w.L0, n, w.psi0A, w.psiA);
+    psi_init_kernel<<<dim3(nb2, nfl > 0 ? nfl : 1), 256, 0, st>>>(w.L0, n, w.psi0A, nfl > 0 ? w.psiA : w.tmp0 - so, f_lo);
     SPYB_LAUNCH_CHECK("psi_init_kernel"); count_launch();
 
     zd* psi = w.psiA;
@@ -1150,13 +1164,21 @@ int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double r
     double err = INFINITY;
     int it = 0;
     for (it = 0; it < n_iter; ++it) {
-        // g = psi^-1 U (psi^-1 U)^H                          (wilson_sf.py:80-87)
-        if (run_gesv(psi, n2, w.Lchol, n2, w.Aw, n2, w.X, n2, n, nf, w.info, st)) return 1;
         zd* g = w.Aw;
-        if (run_gemm<1, 0>(w.X, n2, w.X, n2, g, n2, nullptr, 0, nullptr, n, nf, true, st)) return 1;
-        // [g + I]+                                           (wilson_sf.py:94, 154-184)
-        plus_pack_kernel<<<dim3(eb, len), 128, 0, st>>>(g, nf, n, w.tab, E, w.fftA);
-        SPYB_LAUNCH_CHECK("plus_pack_kernel"); count_launch();
+        if (nfl > 0) {
+            // g = psi^-1 U (psi^-1 U)^H                      (wilson_sf.py:80-87)
+            if (run_gesv(psi + so, n2, w.Lchol + so, n2, w.Aw + so, n2, w.X + so, n2, n, nfl, w.info + f_lo, st)) return 1;
+            if (run_gemm<1, 0>(w.X + so, n2, w.X + so, n2, g + so, n2, nullptr, 0, nullptr, n, nfl, true, st)) return 1;
+            // [g + I]+                                       (wilson_sf.py:94, 154-184)
+            plus_pack_kernel<<<dim3(eb, nfl), 128, 0, st>>>(g, nf, n, w.tab, E, w.fftA, f_lo);
+            SPYB_LAUNCH_CHECK("plus_pack_kernel"); count_launch();
+            if (mrows > 0) {
+                plus_pack_kernel<<<dim3(eb, mrows), 128, 0, st>>>(g, nf, n, w.tab, E, w.fftA, mrow0);
+                SPYB_LAUNCH_CHECK("plus_pack_kernel"); count_launch();
+            }
+        }
+        if (exchange && exchange(exchange_ctx, 0, w.fftA, E * (long long)sizeof(zd), len))
+            return fail("wilson_sf: the exchange callback failed while gathering the packed spectra");
         zd* lag = nullptr;
         if (fft_axis0(w.fftA, w.fftB, w.tw, len, E, plan, &lag, st)) return 1;
         zd* other = lag == w.fftA ? w.fftB : w.fftA;
@@ -1165,31 +1187,37 @@ int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double r
         zd* gp = nullptr;
         if (fft_axis0(other, lag, w.tw, len, E, plan, &gp, st)) return 1;
         zd* M = w.X;
-        plus_unpack_kernel<<<dim3(eb, nf), 128, 0, st>>>(gp, nf, n, w.tab, E, w.g0, M);
-        SPYB_LAUNCH_CHECK("plus_unpack_kernel"); count_launch();
-        // psi <- psi (gplus + S), psi0 <- psi0 (gplus_0 + S)  (wilson_sf.py:101-102)
-        if (run_gemm<0, 0>(psi, n2, M, n2, psi_next, n2, nullptr, 0, nullptr, n, nf, false, st)) return 1;
+        SPYB_CUDA(cudaMemsetAsync(w.err_bits, 0, sizeof(unsigned long long), st));
+        if (nfl > 0) {
+            plus_unpack_kernel<<<dim3(eb, nfl), 128, 0, st>>>(gp, nf, n, w.tab, E, w.g0, M, f_lo);
+            SPYB_LAUNCH_CHECK("plus_unpack_kernel"); count_launch();
+            // psi <- psi (gplus + S)                         (wilson_sf.py:101)
+            if (run_gemm<0, 0>(psi + so, n2, M + so, n2, psi_next + so, n2, nullptr, 0, nullptr, n, nfl, false, st)) return 1;
+        }
+        // psi0 <- psi0 (gplus_0 + S)                         (wilson_sf.py:102), replicated
         if (run_gemm<0, 0>(psi0, 0, w.M0, 0, psi0_next, 0, nullptr, 0, nullptr, n, 1, false, st)) return 1;
         { zd* t = psi; psi = psi_next; psi_next = t; }
         { zd* t = psi0; psi0 = psi0_next; psi0_next = t; }
         // err = max |CSD - psi psi^H| / |CSD|                 (wilson_sf.py:104-106)
-        SPYB_CUDA(cudaMemsetAsync(w.err_bits, 0, sizeof(unsigned long long), st));
         // S and psi psi^H are Hermitian: the upper tiles carry every value of |S - psi psi^H| / |S|
-        if (run_gemm<1, 1>(psi, n2, psi, n2, nullptr, 0, S, n2, w.err_bits, n, nf, true, st)) return 1;
+        if (nfl > 0 && run_gemm<1, 1>(psi + so, n2, psi + so, n2, nullptr, 0, S + so, n2, w.err_bits, n, nfl, true, st)) return 1;
+        if (exchange && exchange(exchange_ctx, 1, w.err_bits, 8, 1))
+            return fail("wilson_sf: the exchange callback failed while reducing the error");
         unsigned long long bits = 0;
         SPYB_CUDA(cudaMemcpyAsync(&bits, w.err_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
         SPYB_CUDA(cudaStreamSynchronize(st));
         memcpy(&err, &bits, sizeof(err));
         if (err < rtol) { converged = true; ++it; break; }
     }
-    if (check_info(w.info, nf, "wilson_sf (inverse of psi)", st)) return 1;
+    if (nfl > 0 && check_info(w.info + f_lo, nfl, "wilson_sf (inverse of psi)", st)) return 1;
     // Sigma = psi0 psi0^T, H = psi psi0^-1                   (wilson_sf.py:114-118)
     if (run_gemm<1, 0>(psi0, 0, psi0, 0, w.tmp0, 0, nullptr, 0, nullptr, n, 1, false, st)) return 1;
     real_part_kernel<<<nb2, 256, 0, st>>>(w.tmp0, Sigma_out, n2);
     SPYB_LAUNCH_CHECK("real_part_kernel"); count_launch();
     if (run_gesv(psi0, 0, w.eye, 0, w.tmp0, 0, w.inv0, 0, n, 1, w.info + nf, st)) return 1;
     if (check_info(w.info + nf, 1, "wilson_sf (inverse of psi0)", st)) return 1;
-    if (run_gemm<0, 0>(psi, n2, w.inv0, 0, static_cast<zd*>(H_out), n2, nullptr, 0, nullptr, n, nf, false, st)) return 1;
+    if (nfl > 0 && run_gemm<0, 0>(psi + so, n2, w.inv0, 0, static_cast<zd*>(H_out) + so, n2, nullptr, 0, nullptr, n, nfl, false, st))
+        return 1;
     *converged_host = converged ? 1 : 0;
     *err_host = err;
     if (iters_host) *iters_host = it;

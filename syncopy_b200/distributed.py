@@ -159,3 +159,48 @@ def get_tile_exchange(engine, n_freq, n_chan, group=None):
     if key not in _exchanges:
         _exchanges[key] = TileExchange(engine, n_freq, n_chan, group)
     return _exchanges[key]
+
+
+class WilsonExchange:
+    """
+    The two collectives of the frequency-slab sharded Wilson factorisation (`spyb_wilson_sharded`) on
+    torch.distributed: (0) every rank broadcasts the rows of the lag-domain work array it packed -- its slab and the
+    slab's mirror image --, (1) the error scalar is max-reduced.  Everything is enqueued on torch's current stream,
+    which is also the stream the library works on, so no host synchronisation is added.
+    """
+
+    def __init__(self, engine, n_freq, group):
+        self.eng, self.group = engine, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.f_begin = freq_slabs(int(n_freq), self.world)
+        self.slab = (self.f_begin[self.rank], self.f_begin[self.rank + 1])
+        self.n_freq = int(n_freq)
+        self._views = {}
+
+    def _view(self, ptr, n_float64):
+        key = (ptr, n_float64)
+        if key not in self._views:
+            self._views[key] = torch.as_tensor(_RawCuda(ptr, (n_float64,), "<f8"), device=self.eng.tdev)
+        return self._views[key]
+
+    def row_ranges(self, r):
+        """Row ranges [a, b) of the full circle (2(nF-1) rows) that rank r packs."""
+        lo, hi = self.f_begin[r], self.f_begin[r + 1]
+        length = 2 * (self.n_freq - 1)
+        out = [(lo, hi)] if hi > lo else []
+        m_lo, m_hi = max(lo, 1), min(hi, self.n_freq - 1)
+        if m_hi > m_lo:
+            out.append((length - m_hi + 1, length - m_lo + 1))
+        return out
+
+    def __call__(self, what, buf, row_bytes, n_rows):
+        if what == 0:
+            per_row = row_bytes // 8
+            full = self._view(buf, per_row * n_rows).view(n_rows, per_row)
+            for r in range(self.world):
+                for a, b in self.row_ranges(r):
+                    dist.broadcast(full[a:b], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                                   group=self.group)
+        elif what == 1:
+            dist.all_reduce(self._view(buf, 1), op=dist.ReduceOp.MAX, group=self.group)
+        return 0

@@ -361,10 +361,14 @@ class Engine:
             factor = int(factor)
         return out, factor, cond0.value
 
-    def wilson_sf(self, csd, n_iter=100, rtol=1e-6):
+    def wilson_sf(self, csd, n_iter=100, rtol=1e-6, slab=None, exchange=None):
         """
         csd [nF, C, C] complex128 CUDA (one-sided) -> (H [nF, C, C] complex128, Sigma [C, C] float64,
         converged, err, iterations)  -- wilson_sf.py:16-120.
+
+        With `slab = (f_lo, f_hi)` and `exchange(what, buf_ptr, row_bytes, n_rows) -> int` (see
+        `spyb_wilson_sharded` in include/spyb200.h; `distributed.WilsonExchange` is the torch.distributed one) only
+        the slab is factorised and H is valid for the slab's rows only.
         """
         import ctypes as C
         assert csd.is_cuda and csd.dtype == torch.complex128 and csd.dim() == 3 and csd.is_contiguous()
@@ -374,9 +378,27 @@ class Engine:
         nbytes = self.lib.spyb_wilson_workspace_bytes(nF, Cn)
         ws = self._workspace(nbytes)
         conv, iters, err = C.c_int(0), C.c_int(0), C.c_double(0.0)
-        _lib.check(self.lib.spyb_wilson(csd.data_ptr(), nF, Cn, int(n_iter), float(rtol), H.data_ptr(),
-                                        Sigma.data_ptr(), C.byref(conv), C.byref(err), C.byref(iters),
-                                        ws.data_ptr(), ws.numel(), self.stream()))
+        if exchange is None:
+            _lib.check(self.lib.spyb_wilson(csd.data_ptr(), nF, Cn, int(n_iter), float(rtol), H.data_ptr(),
+                                            Sigma.data_ptr(), C.byref(conv), C.byref(err), C.byref(iters),
+                                            ws.data_ptr(), ws.numel(), self.stream()))
+        else:
+            failure = []
+
+            def _cb(_ctx, what, buf, row_bytes, n_rows):
+                try:
+                    return int(exchange(int(what), int(buf), int(row_bytes), int(n_rows)) or 0)
+                except Exception as exc:      # noqa: BLE001  (must not propagate through the C frame)
+                    failure.append(exc)
+                    return 1
+            cb = _lib.EXCHANGE_FN(_cb)
+            rc = self.lib.spyb_wilson_sharded(csd.data_ptr(), nF, Cn, int(n_iter), float(rtol), H.data_ptr(),
+                                              Sigma.data_ptr(), C.byref(conv), C.byref(err), C.byref(iters),
+                                              ws.data_ptr(), ws.numel(), int(slab[0]), int(slab[1]), cb, None,
+                                              self.stream())
+            if failure:
+                raise failure[0]
+            _lib.check(rc)
         return H, Sigma, bool(conv.value), err.value, iters.value
 
     def granger(self, csd, H, Sigma):

@@ -161,3 +161,18 @@ def test_full_size_factorisation_property(engine):
     assert torch.equal(Sigma, Sigma.T) or nerr(Sigma.cpu().numpy(), Sigma.T.cpu().numpy()) <= 1e-12
     G = engine.granger(S, H, Sc.real.contiguous())
     assert torch.isfinite(G).all() and G.diagonal(dim1=1, dim2=2).abs().max().item() <= 1e-10
+
+
+def test_sharded_entry_point_with_trivial_exchange(engine):
+    """spyb_wilson_sharded with the whole axis as the slab and a no-op exchange == spyb_wilson (callback plumbing,
+    row bookkeeping); the callback sees the lag-domain array (2(nF-1) rows) and the error scalar every iteration."""
+    S = torch.from_numpy(mvar_csd(6, 33, seed=5)).to(engine.tdev)
+    want = engine.wilson_sf(S, n_iter=40, rtol=1e-9)
+    seen = []
+
+    def exchange(what, buf, row_bytes, n_rows):
+        seen.append((what, row_bytes, n_rows))
+        return 0
+    got = engine.wilson_sf(S, n_iter=40, rtol=1e-9, slab=(0, 33), exchange=exchange)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and got[2:] == want[2:]
+    assert seen[0] == (0, 21 * 16, 64) and seen[1] == (1, 8, 1) and len(seen) == 2 * got[4]

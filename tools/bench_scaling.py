@@ -79,7 +79,7 @@ lo, hi = (T * rank) // world, (T * (rank + 1)) // world
 x = torch.randn((hi - lo, 4096, 128), device=dev)
 ms = timed(lambda: keep.__setitem__("a", batched.granger(x, 200., taper="dpss", taper_opt={"NW": 2, "Kmax": 3}, polyremoval=0,
                                                          engine=eng, reduce_group=group)), iters=2)
-report(cfg=4, what="granger K=3, 500 trials sharded + all-reduce, replicated Wilson", ms=ms, trials_per_s=T / ms * 1e3,
+report(cfg=4, what="granger K=3, 500 trials sharded + all-reduce of the CSD sum, Wilson sharded by frequency slab", ms=ms, trials_per_s=T / ms * 1e3,
        wilson_iterations=int(keep["a"][1]["iterations"]))
 if world > 1:
     dist.destroy_process_group()

@@ -67,3 +67,27 @@ def test_freq_slabs_cover_the_axis():
             assert fb[0] == 0 and fb[-1] == n_freq and len(fb) == world + 1
             sizes = [fb[i + 1] - fb[i] for i in range(world)]
             assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
+
+
+def test_wilson_exchange_rows_partition_the_circle():
+    """Every row of the lag-domain array (2(nF-1) rows) is packed by exactly one rank: its slab plus the mirror image
+    of the slab's interior (the bookkeeping `spyb_wilson_sharded` and `WilsonExchange` must agree on)."""
+    from syncopy_b200.distributed import WilsonExchange, freq_slabs
+    for n_freq in (2, 3, 9, 33, 2049):
+        for world in (1, 2, 3, 8):
+            wx = WilsonExchange.__new__(WilsonExchange)
+            wx.n_freq, wx.world = n_freq, world
+            wx.f_begin = freq_slabs(n_freq, world)
+            length = 2 * (n_freq - 1)
+            owner = [0] * length
+            for r in range(world):
+                lo, hi = wx.f_begin[r], wx.f_begin[r + 1]
+                rows = wx.row_ranges(r)
+                # the library's formula (csrc/wilson.cu): mirror rows [len - m_hi + 1, len - m_lo + 1)
+                m_lo, m_hi = max(lo, 1), min(hi, n_freq - 1)
+                want = ([(lo, hi)] if hi > lo else []) + ([(length - m_hi + 1, length - m_lo + 1)] if m_hi > m_lo else [])
+                assert rows == want
+                for a, b in rows:
+                    for i in range(a, b):
+                        owner[i] += 1
+            assert owner == [1] * length, (n_freq, world)

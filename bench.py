@@ -37,6 +37,17 @@ METRIC = "trial-spectra/s (mtmfft+CSD coherence, 256ch/4096smp)"
 UNIT = "trial-spectra/s"
 
 
+def _trial_seeds(n_trials, seed=42):
+    """Per-trial seeds as the reference's synthdata draws them (synthdata/utils.py:53-55, tests/helpers.py:18)."""
+    return np.random.default_rng(seed).integers(1_000_000, size=n_trials)
+
+
+def _white_noise_trial(n_samples, n_channels, seed):
+    """White-noise trial as syncopy.synthdata.white_noise generates it (synthdata/analog.py:38-40).  The GPU arm
+    makes its own inputs: nothing under oracle/ is imported outside the CPU-baseline / reference legs."""
+    return np.random.default_rng(seed).normal(size=(n_samples, n_channels)).astype("f4")
+
+
 def workload_cfg(taper):
     if taper == "dpss":
         # tapsmofrq = 4*fs/4096 -> NW = 4, Kmax = 7 (SURVEY.md 8d)
@@ -253,7 +264,6 @@ def load_peaks():
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from oracle import synth                       # input generator only (checker-side code)
     from syncopy_b200 import _lib, batched
     from syncopy_b200 import hostmath as hm
     from syncopy_b200.engine import get_engine
@@ -271,11 +281,11 @@ def run_gpu_arm(args):
     K = w["K"]
 
     # ---- synthetic trials: white noise, per-trial seeds as syncopy.synthdata (seed 42), shard = rank
-    seeds = synth.trial_seeds(N_TRIALS * world)[rank * N_TRIALS:(rank + 1) * N_TRIALS]
+    seeds = _trial_seeds(N_TRIALS * world)[rank * N_TRIALS:(rank + 1) * N_TRIALS]
     host = torch.empty((N_TRIALS, N_SAMPLES, N_CHAN), dtype=torch.float32).pin_memory()
     hnp = host.numpy()
     for k, s in enumerate(seeds):
-        hnp[k] = synth.white_noise_trial(N_SAMPLES, N_CHAN, int(s))
+        hnp[k] = _white_noise_trial(N_SAMPLES, N_CHAN, int(s))
     x = host.to(dev)
 
     n_freq = N_SAMPLES // 2 + 1

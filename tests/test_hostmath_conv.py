@@ -1,0 +1,79 @@
+"""
+Host side of the wavelet / superlet kernels, checked on the CPU: the convolution plan the engine uploads
+(`hostmath.conv_same_length`, `conv_same_spectrum`, `cwt_taps`, `superlet_taps`, `compute_functions.superlet_tables`)
+is evaluated here with NumPy FFTs -- the arithmetic `cwt_kernel` performs on the device -- and must reproduce the
+oracle's `fftconvolve(..., 'same')` transforms, including kernels longer than the trial.
+"""
+import numpy as np
+import pytest
+
+from oracle import synth
+from oracle import timefreq as otf
+from syncopy_b200 import hostmath as hm
+from syncopy_b200.compute_functions import superlet_tables
+
+
+def plan_transform(x, taps_per_scale, exponents):
+    """NumPy emulation of Engine.conv_plan + cwt_kernel for one trial x [N, C] -> [nScales, N, C] complex128."""
+    n = x.shape[0]
+    flat = [t for tl in taps_per_scale for t in tl]
+    L = hm.conv_same_length(n, flat)
+    X = np.fft.fft(np.concatenate([x.astype(np.float64), np.zeros((L - n, x.shape[1]))]), axis=0)
+    out = []
+    for tl, el in zip(taps_per_scale, exponents):
+        z = np.ones((n, x.shape[1]), dtype=np.complex128)
+        for taps, a in zip(tl, el):
+            kern = hm.conv_same_spectrum(taps, n, L)             # FFT_L(h) / L
+            y = np.fft.ifft(X * (kern * L)[:, None], axis=0)[:n]
+            z = z * (y if a == 1.0 else np.abs(y) ** a * np.exp(1j * a * np.angle(y)))
+        out.append(z)
+    return np.stack(out)
+
+
+def nerr(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("wav_o,wav_g", [(otf.Morlet(6), hm.Morlet(6)), (otf.Paul(4), hm.Paul(4)),
+                                         (otf.DOG(2), hm.DOG(2))])
+@pytest.mark.parametrize("n", [300, 512])
+def test_cwt_plan_reproduces_fftconvolve_same(wav_o, wav_g, n):
+    fs = 200.
+    x = synth.white_noise_trial(n, 3, 11)
+    foi = np.array([1.5, 7., 30., 90.])                 # the lowest one has a support far beyond the trial
+    scales = wav_o.scale_from_period(1 / foi)
+    if isinstance(wav_g, hm.Morlet):
+        assert len(hm.cwt_taps(wav_g, scales[0], 1 / fs)) > n
+    want = otf.cwt(x.astype(np.float64), wav_o, scales, 1 / fs)
+    got = plan_transform(x, [[hm.cwt_taps(wav_g, s, 1 / fs)] for s in scales], [[1.0]] * scales.size)
+    assert got.shape == want.shape
+    assert nerr(got, want) <= 1e-6                       # the oracle rounds to complex64
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_superlet_plan_reproduces_reference_bookkeeping(adaptive):
+    fs, n = 500., 400
+    x = synth.white_noise_trial(n, 2, 5)
+    foi = np.arange(10., 100., 20.)
+    scales = 1.0 / (2 * np.pi * foi)
+    if adaptive:
+        scales = np.sort(scales)[::-1]                   # FASLT wants high -> low scales (freqanalysis.py:940-950)
+    kw = dict(order_max=6, order_min=1, c_1=3, adaptive=adaptive)
+    want = otf.superlet(x.copy(), fs, scales, **kw)
+    taps, expo = superlet_tables(scales, 1 / fs, **kw)
+    got = plan_transform(x, taps, expo)
+    assert got.shape == want.shape
+    # magnitudes: the reference multiplies complex64 powers, so 1e-5; phases only where the magnitude is not tiny
+    assert nerr(np.abs(got), np.abs(want)) <= 2e-5
+    big = np.abs(want) > 1e-3 * np.abs(want).max()
+    assert np.abs(np.angle(got[big] * np.conj(want[big]))).max() <= 1e-3
+
+
+def test_conv_same_length_is_minimal_power_of_two():
+    n = 1000
+    for m in (1, 2, 7, 999, 1000, 1001, 5000, 40001):
+        taps = np.ones(m)
+        L = hm.conv_same_length(n, [taps])
+        c0 = (m - 1) // 2
+        need = n + max(min(c0, n - 1), min(m - 1 - c0, n - 1))
+        assert L >= need and (L & (L - 1)) == 0 and (L // 2 < need or L == 16)

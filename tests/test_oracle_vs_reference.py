@@ -70,3 +70,45 @@ def test_superlet_cwt_live(ref):
     w = ref.wavelets_mod.Morlet(6)
     sc = w.scale_from_period(1 / np.array([5., 20., 80.]))
     assert nerr(otf.wavelet(x.copy(), 500., sc, otf.Morlet(6)), ref.wavelet.wavelet(x.copy(), 500., sc, w)) <= 1e-7
+
+
+def _mvar_like_csd(n_chan, n_freq, seed):
+    """Well-conditioned Hermitian positive-definite spectral matrices (one-sided), real at DC and Nyquist."""
+    rng = np.random.default_rng(seed)
+    a1 = 0.4 * np.eye(n_chan) + 0.2 / np.sqrt(n_chan) * rng.normal(size=(n_chan, n_chan))
+    q = rng.normal(size=(n_chan, n_chan))
+    sigma = q @ q.T / n_chan + np.eye(n_chan)
+    om = np.pi * np.arange(n_freq) / (n_freq - 1)
+    Hf = np.linalg.inv(np.eye(n_chan)[None] - a1[None] * np.exp(-1j * om)[:, None, None])
+    S = Hf @ sigma[None] @ Hf.conj().transpose(0, 2, 1)
+    return 0.5 * (S + S.conj().transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("n_chan,n_freq", [(2, 33), (5, 26), (9, 65)])
+def test_wilson_granger_live(ref, n_chan, n_freq):
+    S = _mvar_like_csd(n_chan, n_freq, n_chan)
+    H, Sig, conv, err = ref.wilson_sf.wilson_sf(S.copy(), nIter=80, rtol=1e-9)
+    H2, Sig2, conv2, err2 = oc.wilson_sf(S.copy(), nIter=80, rtol=1e-9)
+    assert conv == conv2 and nerr(H2, H) <= 1e-12 and nerr(Sig2, Sig) <= 1e-12
+    assert nerr(oc.granger(S, H2, Sig2), ref.granger.granger(S, H, Sig)) <= 1e-12
+    # iteration cap: not converged is a normal return, identical partial result
+    Hc, Sc, cc, ec = ref.wilson_sf.wilson_sf(S.copy(), nIter=2, rtol=1e-14)
+    Hc2, Sc2, cc2, ec2 = oc.wilson_sf(S.copy(), nIter=2, rtol=1e-14)
+    assert (cc, cc2) == (False, False) and nerr(Hc2, Hc) <= 1e-12 and abs(ec - ec2) <= 1e-12 * ec
+
+
+@pytest.mark.parametrize("cond_max,scale", [(1e3, 1.0), (5.0, 1e-2), (3.0, 1e-4), (10.0, 1e3)])
+def test_regularize_live(ref, cond_max, scale):
+    S = (_mvar_like_csd(6, 20, 6) * scale).astype(np.complex64)
+    want = ref.wilson_sf.regularize_csd(S.copy(), cond_max=cond_max, eps_max=1e-1)
+    got = oc.regularize_csd(S.copy(), cond_max=cond_max, eps_max=1e-1)
+    assert got[1] == want[1] and float(got[2]) == float(want[2])
+    assert np.array_equal(np.asarray(got[0]), np.asarray(want[0]))
+
+
+def test_normalize_csd_live(ref):
+    S = _mvar_like_csd(4, 17, 2).astype(np.complex64)
+    for output in ("abs", "pow", "fourier", "real", "imag", "angle", "absreal", "absimag"):
+        want = ref.csd.normalize_csd(S.copy(), output)
+        got = oc.normalize_csd(S.copy(), output)
+        assert got.dtype == want.dtype and nerr(got, want) <= 1e-12

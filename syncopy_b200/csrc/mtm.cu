@@ -357,6 +357,8 @@ int mtm_frames(const MtmFramesDesc& d, cudaStream_t stream) {
     // windows (several frames per block) and Bluestein lengths on the Stockham kernel below
     static const bool force_stockham = getenv("SPYB_MTM_STOCKHAM") != nullptr;
     if (!pl->bluestein && !force_stockham) {
+        const int rt = mtm_launch_tma(pl->log2n, a, stream);
+        if (rt >= 0) return rt;
         const int rc = mtm_launch_dif(pl->log2n, a, stream);
         if (rc >= 0) return rc;
     }

@@ -34,5 +34,7 @@ struct MtmArgs {
 
 // mtm_dif.cu: returns -1 when the shape is not handled there (the caller then uses the Stockham kernel)
 int mtm_launch_dif(int log2n, const MtmArgs& a, cudaStream_t stream);
+// mtm_tma.cu: persistent TMA-pipelined kernel for N = 4096 and full 8-channel tiles; -1 when not eligible
+int mtm_launch_tma(int log2n, const MtmArgs& a, cudaStream_t stream);
 
 }  // namespace spyb

@@ -4,16 +4,23 @@ bench.py -- headline benchmark of the hot path on BASELINE.json's metric:
 
     trial-spectra/s for mtmfft + ST_CrossSpectra coherence on 200 trials x 256 channels x
     4096 samples float32 per GPU (BASELINE configs[1]; weak scaling over GPUs: every rank
-    owns 200 trials, the trial-summed CSD is all-reduced over NCCL, then normalised).
+    owns 200 trials, the trial-summed cross spectra are exchanged tile by tile over NVLink,
+    then normalised per frequency slab).
 
 One "step" = one full pass over the rank's 200 synthetic trials:
-    tapered FFT (K1) -> cross-spectral contraction over all trials (K2) -> [all-reduce] ->
-    coherency |C_ij| (K3).
+    tapered FFT (K1) -> cross-spectral contraction over all trials (K2) -> [exchange] ->
+    coherency |C_ij| (K3; fused into K2's epilogue on one rank).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--taper hann|dpss] [--impl ours|reference]
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric
 through the public API with pinned host buffers and H2D / D2H copies inside the timed region.
+Besides the contract keys the line carries
+  * `parity`   -- the coherence of THIS run against a float64 direct-DFT reference computed here on a few
+                  frequencies (N = 1 and N > 1; normwise error, north-star bar 1e-5);
+  * `configs`  -- device-resident time, algorithmic bytes / flops, roofline fraction and a bounded
+                  CPU sample for BASELINE cfg-3 (mtmconvol), cfg-4 (Granger) and cfg-5 (wavelet / superlet);
+  * `strong_scaling` (N > 1) -- the same step with 200 trials in TOTAL split over the ranks.
 `--impl reference` times the reference's own CPU algorithm (the NumPy oracle port, one process
 per host core, one task per trial like its Dask path) on a bounded sample of the same workload.
 """
@@ -96,91 +103,197 @@ def _cpu_worker(job):
     return wid
 
 
-_FIXED_COST = {}
-
-
-def cpu_reference_sample(taper, n_workers=None, trials_per_worker=1):
+class CpuReference:
     """
-    The reference algorithm (oracle port) on the host cores, on a bounded sample of the workload:
-    one process per worker, one task per trial like the reference's Dask path
-    (computational_routine.py:926-930), every worker summing its trials in place, then the parent adds the
-    partial sums, divides by the trial count and runs normalize_csd once (connectivity_analysis.py:677-679).
-    The per-trial cost measured under full parallel load and the once-per-job cost (reduction + normalisation,
-    measured on the first call and reused) are combined into the throughput of the full 200-trial job:
-        value = 200 / (ceil(200 / workers) * t_trial + t_once).
+    The reference algorithm (oracle port) on the host cores: one process per worker, one task per trial like the
+    reference's Dask path (computational_routine.py:926-930), every worker summing its trials in place; the parent
+    adds the partial sums, divides by the trial count and runs normalize_csd once
+    (connectivity_analysis.py:677-679).
+
+    `sample(rounds)` TIMES `rounds` real pool rounds (workers x rounds trials); its wall clock is what the reference
+    arm reports as `ms_per_step` and `value` (= trials of the sample / measured seconds: the trial stage alone, which
+    favours the CPU side -- the once-per-job reduction + normalisation is not in it).  `job_model()` adds the
+    measured once-per-job cost and extrapolates to the 200-trial job; that figure is labelled as a model.
     """
-    import mmap
-    from oracle import connectivity as oc
-    from oracle import synth
-    w = workload_cfg(taper)
-    cores = os.cpu_count() or 1
-    try:
-        import psutil
-        mem_gb = psutil.virtual_memory().available / 2 ** 30
-    except Exception:
-        mem_gb = 64
-    per_proc_gb = 5.6 + 1.1 * w["K"]          # [K, F, C, C] complex64 temporaries + the partial sum
-    if n_workers is None:
-        n_workers = int(max(1, min(cores, 32, (mem_gb - 4) // per_proc_gb)))
-    n_freq = N_SAMPLES // 2 + 1
-    n_trials = n_workers * trials_per_worker
-    seeds = synth.trial_seeds(n_trials)
-    nbytes = n_workers * n_freq * N_CHAN * N_CHAN * 8
-    buf = mmap.mmap(-1, nbytes)                # anonymous shared mapping, inherited by the forked workers
-    _SHARED["partials"] = np.frombuffer(buf, dtype=np.complex64).reshape(n_workers, n_freq, N_CHAN, N_CHAN)
-    jobs = [(i, [int(sd) for sd in seeds[i::n_workers]], w["taper"], w["taper_opt"]) for i in range(n_workers)]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(n_workers) as pool:
-        t0 = time.perf_counter()
-        list(pool.imap_unordered(_cpu_worker, jobs))
-        t_pool = time.perf_counter() - t0
-    t_trial = t_pool / trials_per_worker
-    key = (taper, n_workers)
-    if key not in _FIXED_COST:
-        t0 = time.perf_counter()
-        acc = _SHARED["partials"][0].copy()
-        for i in range(1, n_workers):
-            acc += _SHARED["partials"][i]
-        acc /= n_trials
-        coh = oc.normalize_csd(acc, "abs")
-        _FIXED_COST[key] = time.perf_counter() - t0
-        assert np.isfinite(coh).all()
-        del acc, coh
-    t_once = _FIXED_COST[key]
-    _SHARED.clear()
-    del buf
-    rounds = -(-N_TRIALS // n_workers)
-    job_s = rounds * t_trial + t_once
-    return dict(value=N_TRIALS / job_s, unit=UNIT, cores=n_workers, kind="port",
-                sample=f"{n_trials} trials ({trials_per_worker}/worker, one process per worker, 1 BLAS thread "
-                       f"each): {t_trial:.2f} s per trial and worker under load; partial-sum reduction + trial mean "
-                       f"+ normalize_csd once per job: {t_once:.1f} s; extrapolated to the {N_TRIALS}-trial job = "
-                       f"{rounds} rounds x {t_trial:.2f} s + {t_once:.1f} s = {job_s:.1f} s"), t_pool
+
+    def __init__(self, taper, n_workers=None):
+        import mmap
+        self.w = workload_cfg(taper)
+        cores = os.cpu_count() or 1
+        try:
+            import psutil
+            mem_gb = psutil.virtual_memory().available / 2 ** 30
+        except Exception:
+            mem_gb = 64
+        per_proc_gb = 5.6 + 1.1 * self.w["K"]          # [K, F, C, C] complex64 temporaries + the partial sum
+        if n_workers is None:
+            n_workers = int(max(1, min(cores, 32, (mem_gb - 4) // per_proc_gb)))
+        self.n_workers = n_workers
+        self.n_freq = N_SAMPLES // 2 + 1
+        nbytes = n_workers * self.n_freq * N_CHAN * N_CHAN * 8
+        self._buf = mmap.mmap(-1, nbytes)              # anonymous shared mapping, inherited by the forked workers
+        self.partials = np.frombuffer(self._buf, dtype=np.complex64).reshape(n_workers, self.n_freq, N_CHAN, N_CHAN)
+        self.t_once = None
+        self.last = None
+
+    def sample(self, rounds=1):
+        from oracle import synth
+        n_trials = self.n_workers * rounds
+        seeds = synth.trial_seeds(n_trials)
+        _SHARED["partials"] = self.partials
+        jobs = [(i, [int(sd) for sd in seeds[i::self.n_workers]], self.w["taper"], self.w["taper_opt"])
+                for i in range(self.n_workers)]
+        ctx = mp.get_context("fork")
+        with ctx.Pool(self.n_workers) as pool:
+            t0 = time.perf_counter()
+            list(pool.imap_unordered(_cpu_worker, jobs))
+            t_pool = time.perf_counter() - t0
+        self.last = dict(trials=n_trials, seconds=t_pool, rounds=rounds)
+        return n_trials, t_pool
+
+    def once_per_job(self):
+        """partial-sum reduction + trial mean + normalize_csd, measured once (single-threaded like the reference)"""
+        from oracle import connectivity as oc
+        if self.t_once is None:
+            t0 = time.perf_counter()
+            acc = self.partials[0].copy()
+            for i in range(1, self.n_workers):
+                acc += self.partials[i]
+            acc /= max(1, self.last["trials"])
+            coh = oc.normalize_csd(acc, "abs")
+            self.t_once = time.perf_counter() - t0
+            assert np.isfinite(coh).all()
+        return self.t_once
+
+    def job_model(self):
+        t_round = self.last["seconds"] / self.last["rounds"]
+        t_once = self.once_per_job()
+        n_rounds = -(-N_TRIALS // self.n_workers)
+        job_s = n_rounds * t_round + t_once
+        return dict(value=N_TRIALS / job_s, job_seconds=job_s,
+                    how=f"MODEL, not a timed job: {n_rounds} pool rounds x {t_round:.2f} s (measured per round under "
+                        f"full load) + {t_once:.1f} s once per job (partial-sum reduction + trial mean + "
+                        f"normalize_csd, measured)")
+
+    def info(self):
+        n, s = self.last["trials"], self.last["seconds"]
+        return dict(value=n / s, unit=UNIT, cores=self.n_workers, kind="port",
+                    sample=f"{n} trials = {self.last['rounds']} timed pool round(s) x {self.n_workers} workers (one "
+                           f"process per worker, 1 BLAS thread each, one task per trial): {s:.2f} s wall clock; trial "
+                           f"stage only (per-trial mtmfft + cross spectra + local trial sum)")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    vals, times = [], []
-    info = None
+    ref = CpuReference(args.taper)
+    rounds = 2
+    vals, secs = [], []
     for i in range(args.warmup + args.steps):
-        info, dt = cpu_reference_sample(args.taper)
+        n, s = ref.sample(rounds)
         if i >= args.warmup:
-            vals.append(info["value"])
-            times.append(dt)
+            vals.append(n / s)
+            secs.append(s)
     value = float(np.mean(vals))
+    info = ref.info()
     info["value"] = value
+    model = ref.job_model()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * N_TRIALS / value,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (FFT in f64, CSD in c64)",
         "data": "synthetic", "config": config_dict(args, args.gpus), "cpu_baseline": info,
+        "step_definition": f"one step = {rounds} real pool rounds = {rounds * ref.n_workers} trials of the workload "
+                           f"(bounded sample); ms_per_step is its measured wall clock",
+        "full_job_model": model,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(json.dumps(line))
     return 0
+
+
+# ---- bounded CPU samples for the other BASELINE configs (oracle port, one host core each) -------------------------
+
+def _cpu_cfg3():
+    from oracle import spectral as osp
+    from oracle import synth
+    x = synth.white_noise_trial(16384, 128, 7)
+    t0 = time.perf_counter()
+    ftr, _ = osp.mtmconvol(x, 1024., 512, 256, "dpss", {"NW": 4, "Kmax": 7}, "zeros", True, "constant")
+    p = (ftr * ftr.conj()).real.astype("f4").mean(axis=1)
+    dt = time.perf_counter() - t0
+    return dict(value=1.0 / dt, unit="trials/s", cores=1, kind="port",
+                sample=f"1 trial (16384 x 128, 7 tapers) through oracle mtmconvol + pow + taper mean: {dt:.2f} s; "
+                       f"checksum {float(p.sum()):.4e}")
+
+
+def _cpu_cfg5(which):
+    from oracle import timefreq as otf
+    from oracle import synth
+    foi = np.arange(1., 101., 2.)
+    if which == "wavelet":
+        x = synth.white_noise_trial(8192, 64, 9)
+        wav = otf.Morlet(6)
+        t0 = time.perf_counter()
+        spec = otf.wavelet(x, 1000., wav.scale_from_period(1 / foi), wav)
+        p = (spec * spec.conj()).real
+        dt = time.perf_counter() - t0
+        return dict(value=1.0 / dt, unit="trials/s", cores=1, kind="port",
+                    sample=f"1 trial (8192 x 64, Morlet, 50 scales): {dt:.2f} s; checksum {float(p.sum()):.4e}")
+    nch = 4                                                   # superlets: ~30-60 s per 64-channel trial and core
+    x = synth.white_noise_trial(8192, nch, 9)
+    scales = 1.0 / (2 * np.pi * foi)
+    adaptive = which == "superlet_faslt"
+    sc = scales[::-1].copy() if adaptive else scales
+    t0 = time.perf_counter()
+    spec = otf.superlet(x, 1000., sc, 10, 1, 3, adaptive)
+    p = (spec * spec.conj()).real
+    dt = time.perf_counter() - t0
+    return dict(value=1.0 / (dt * 64 / nch), unit="trials/s", cores=1, kind="port",
+                sample=f"{nch} of 64 channels of 1 trial (8192 smp, orders 1-10, {'FASLT' if adaptive else 'multiplicative'}): "
+                       f"{dt:.2f} s, scaled x{64 // nch} to a 64-channel trial (the transform is per channel); "
+                       f"checksum {float(p.sum()):.4e}")
+
+
+def _cpu_cfg4():
+    """one trial of the CSD stage, one condition-number pass and one Wilson iteration of the oracle at cfg-4's shape"""
+    from oracle import connectivity as oc
+    from oracle import synth
+    x = synth.white_noise_trial(4096, 128, 3)
+    t0 = time.perf_counter()
+    cs, _ = oc.cross_spectra_cF(x, 200., taper="dpss", taper_opt={"NW": 2, "Kmax": 3}, demean_taper=True, polyremoval=0)
+    t_trial = time.perf_counter() - t0
+    csd = cs[0].astype(np.complex128) + 0.5 * np.eye(128)[None]         # a single-trial CSD is rank 3: make it PD
+    t0 = time.perf_counter()
+    c = np.linalg.cond(csd.astype(np.complex64)).max()
+    t_cond = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oc.wilson_sf(csd, nIter=1, rtol=1e-9)
+    t_iter = time.perf_counter() - t0
+    return dict(value=None, unit="s", cores=1, kind="port", t_trial_s=t_trial, t_cond_s=t_cond, t_wilson_1iter_s=t_iter,
+                sample=f"1 trial of the CSD stage (4096 x 128, K=3): {t_trial:.2f} s; one np.linalg.cond pass over "
+                       f"2049 x 128 x 128: {t_cond:.2f} s (max {c:.3g}); wilson_sf with nIter=1 (initialisation + one "
+                       f"iteration): {t_iter:.2f} s")
+
+
+def cpu_config_samples():
+    """run the bounded samples side by side in a small pool (one core each)"""
+    jobs = [("cfg3", _cpu_cfg3, ()), ("cfg5_wavelet", _cpu_cfg5, ("wavelet",)),
+            ("cfg5_superlet", _cpu_cfg5, ("superlet",)), ("cfg5_superlet_faslt", _cpu_cfg5, ("superlet_faslt",)),
+            ("cfg4", _cpu_cfg4, ())]
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    out = {}
+    ctx = mp.get_context("fork")
+    with ctx.Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        res = [(name, pool.apply_async(fn, a)) for name, fn, a in jobs]
+        for name, r in res:
+            try:
+                out[name] = r.get(timeout=600)
+            except Exception as exc:      # noqa: BLE001
+                out[name] = {"error": repr(exc)}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -244,7 +357,8 @@ class ClockSampler:
 
 
 def load_traffic(kernel, taper):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/ncu_traffic.json; the
+    entry names the capture it came from -- a constant of that build, not something this run measures)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         return json.load(open(path)).get(f"{kernel}:{taper}")
@@ -261,11 +375,311 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+def float64_coherence_sums(trials, taper, taper_opt, fsel):
+    """
+    Float64 reference of the trial-SUMMED cross spectra on the bins `fsel`, written out here (no library of this
+    repository, no oracle): de-mean, taper, direct DFT of the selected bins, outer product, mean over tapers,
+    sum over trials (mtmfft.py:111-127, csd.py:98-102, computational_routine.py:1022-1032 in float64).
+    Returns complex128 [len(fsel), C, C].
+    """
+    import scipy.signal.windows as sw
+    T, N, C = trials.shape
+    if taper == "dpss":
+        win = np.atleast_2d(sw.dpss(N, NW=taper_opt["NW"], Kmax=int(taper_opt["Kmax"]))) * np.sqrt(N)
+    else:
+        w = getattr(sw, taper)(N)
+        win = (w * np.sqrt(4 / 3) * np.sqrt(N / w.sum()))[None]          # _norm_spec.py:27-46
+    n = np.arange(N)
+    E = np.exp(-2j * np.pi * np.outer(np.asarray(fsel), n) / N)           # [nsel, N]
+    acc = np.zeros((len(fsel), C, C), dtype=np.complex128)
+    for t in range(T):
+        x = trials[t].astype(np.float64)
+        x = x - x.mean(axis=0, keepdims=True)
+        cs = np.zeros_like(acc)
+        for k in range(win.shape[0]):
+            X = E @ (win[k][:, None] * x)                                  # [nsel, C]
+            cs += X[:, :, None] * X[:, None, :].conj()
+        acc += cs / win.shape[0]
+    return acc
+
+
+def _coh_abs(csd_sum):
+    d = np.sqrt(np.abs(np.einsum("fii->fi", csd_sum)))
+    return np.abs(csd_sum) / (d[:, :, None] * d[:, None, :])
+
+
+class Cfg2Step:
+    """One rank's cfg-2 step: K1 -> K2 [-> barrier -> K3], device-resident."""
+
+    def __init__(self, eng, x, args, group, world, rank, total_trials):
+        import torch
+        from syncopy_b200 import hostmath as hm
+        self.eng, self.x, self.group, self.world, self.rank = eng, x, group, world, rank
+        self.total_trials = total_trials
+        self.n_local = x.shape[0]
+        w = workload_cfg(args.taper)
+        self.K = w["K"]
+        dev = eng.tdev
+        self.n_freq = N_SAMPLES // 2 + 1
+        self.tapers = eng.taper_table(w["taper"], N_SAMPLES, N_SAMPLES, w["taper_opt"])
+        self.scale = hm.mtmfft_scale(N_SAMPLES, N_SAMPLES)
+        # default path: tcgen05 contraction writing upper tiles into per-frequency-slab slot buffers (peer stores
+        # over NVLink for N > 1), then per-slab sum + normalisation; --csd-impl 1/3 select the older paths
+        self.mode = {0: "tiles", 2: "tiles", 1: "simt", 3: "planar"}[args.csd_impl]
+        if self.mode == "tiles" and not eng.csd_planar_supported(N_CHAN):
+            self.mode = "simt"
+        # one rank: the contraction's epilogue normalises and mirrors itself (K2 + K3 in one kernel)
+        self.fused = self.mode == "tiles" and world == 1 and args.csd_impl == 0
+        if self.mode == "tiles":
+            from syncopy_b200.distributed import get_tile_exchange
+            self.ex = get_tile_exchange(eng, self.n_freq, N_CHAN, group)
+            self.nf_local = self.ex.nf_local
+            self.f_lo = self.ex.f_begin[self.ex.rank]
+        else:
+            self.nf_local, self.f_lo = self.n_freq, 0
+        rows = max(1, self.n_local * self.K)
+        if self.mode in ("tiles", "planar"):   # planar re|im rows: operand layout of the tcgen05 kernel
+            self.spectra = torch.empty((self.n_freq, rows, 2, N_CHAN), dtype=torch.float32, device=dev)
+        else:
+            self.spectra = torch.empty((self.n_freq, rows, N_CHAN), dtype=torch.complex64, device=dev)
+        self.csd_sum = None if self.mode == "tiles" else torch.empty((self.n_freq, N_CHAN, N_CHAN),
+                                                                     dtype=torch.complex64, device=dev)
+        self.coh = torch.empty((1, self.nf_local, N_CHAN, N_CHAN), dtype=torch.float32, device=dev)
+
+    def step(self, marks=None):
+        import torch.distributed as dist
+        eng, K = self.eng, self.K
+        rec = (lambda i: marks[i].record()) if marks is not None else (lambda i: None)
+        rec(0)
+        eng.mtmfft(self.x, self.tapers, N_SAMPLES, self.scale, polyremoval=0,
+                   output="fourier" if self.mode == "simt" else "fourier_planar", keeptapers=True, out=self.spectra,
+                   freq_major=True)
+        rec(1)
+        if self.fused:
+            eng.csd_coherence_planar(self.spectra, output="abs", out=self.coh[0])
+            for i in (2, 3, 4):
+                rec(i)
+            return
+        if self.mode == "tiles":
+            self.ex.accumulate(self.spectra, alpha=1.0 / K, beta=0.0)
+        elif self.mode == "planar":
+            eng.csd_accumulate_planar(self.spectra, acc=self.csd_sum, alpha=1.0 / K, beta=0.0)
+        else:
+            eng.csd_accumulate(self.spectra, acc=self.csd_sum, alpha=1.0 / K, beta=0.0, impl=1)
+        rec(2)
+        if self.mode == "tiles":
+            self.ex.barrier(self.n_local, n_total=self.total_trials)   # counter all-reduce: every rank's tiles landed
+            rec(3)
+            self.ex.normalize(self.total_trials, output="abs", out=self.coh[0])
+            rec(4)
+            return
+        if self.world > 1:
+            import torch
+            dist.all_reduce(torch.view_as_real(self.csd_sum))
+        rec(3)
+        eng.csd_normalize(self.csd_sum[None], output="abs", pre_scale=1.0 / self.total_trials, out=self.coh)
+        rec(4)
+
+
+def timed_steps(stepper, steps, warmup, barrier, dev, world):
+    """W untimed steps, then exactly `steps` steps between barrier + synchronize; returns (max-over-ranks ms, segments)."""
+    import torch
+    import torch.distributed as dist
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+    for _ in range(warmup):
+        stepper.step()
+    barrier()
+    marks = [[ev() for _ in range(5)] for _ in range(steps)]
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for i in range(steps):
+        stepper.step(marks[i])
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    seg = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(4)] for m in marks])
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    return ms, seg
+
+
+def parity_block(stepper, host_trials, args, world, rank, dev):
+    """
+    Coherence of this run (device-resident path, last timed step) against the float64 reference on a few bins.
+    N > 1: every rank computes the float64 trial sums of ITS trials, the sums are all-reduced (float64, NCCL), and
+    every rank checks the bins of its own frequency slab; the worst error over ranks is reported.
+    """
+    import torch
+    import torch.distributed as dist
+    w = workload_cfg(args.taper)
+    nF = N_SAMPLES // 2 + 1
+    fsel = np.unique(np.concatenate([[0, 1, nF - 2, nF - 1], np.linspace(2, nF - 3, 4 + 2 * max(1, world)).astype(int)]))
+    n_par = host_trials.shape[0]
+    sums = float64_coherence_sums(host_trials[:n_par], w["taper"], w["taper_opt"], fsel)
+    if world > 1:
+        t = torch.from_numpy(np.ascontiguousarray(sums)).to(dev)
+        dist.all_reduce(torch.view_as_real(t))
+        sums = t.cpu().numpy()
+    want = _coh_abs(sums)
+    lo, hi = stepper.f_lo, stepper.f_lo + stepper.nf_local
+    own = [(i, f) for i, f in enumerate(fsel) if lo <= f < hi]
+    err = 0.0
+    if own:
+        got = stepper.coh[0][[f - lo for _, f in own]].cpu().numpy().astype(np.float64)
+        ref = want[[i for i, _ in own]]
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    n_checked = len(own)
+    if world > 1:
+        t = torch.tensor([err, float(n_checked)], dtype=torch.float64, device=dev)
+        e = t[:1].clone()
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        c = t[1:].clone()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        err, n_checked = float(e.item()), int(c.item())
+    return {"max_normwise_err": err, "tolerance": 1e-5, "ok": bool(err <= 1e-5), "bins_checked": n_checked,
+            "bins": [int(f) for f in fsel],
+            "reference": "float64 direct DFT of the selected bins + float64 outer products / trial sum, computed in "
+                         "bench.py (scipy window, numpy) on the same trials" +
+                         ("; per-rank float64 sums all-reduced, every rank checks the bins of its slab" if world > 1 else "")}
+
+
+def dgemm_peak_tflops(dev):
+    """measured FP64 matmul rate (cuBLAS DGEMM 4096^3) -- only a denominator for the Wilson kernels' TFLOP/s"""
+    import torch
+    a = torch.randn((4096, 4096), dtype=torch.float64, device=dev)
+    b = torch.randn((4096, 4096), dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        torch.matmul(a, b)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return 3 * 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
+def configs_block(eng, peaks, world, rank, group, with_cpu):
+    """BASELINE cfg-3 / cfg-4 / cfg-5 on this run's GPUs (device-resident, CUDA events, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from syncopy_b200 import batched, hostmath as hm
+    dev = eng.tdev
+    hbm = peaks["hbm_gbs"]
+    out = {}
+
+    def timed(fn, iters=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    torch.manual_seed(4321 + rank)
+    keep = {}
+    # ---- cfg-3: mtmconvol, 100 trials x 128 ch x 16384 smp per GPU, nperseg 512, hop 256, 7 DPSS tapers, pow, taper mean
+    T, N, C = 100, 16384, 128
+    x = torch.randn((T, N, C), device=dev)
+    kw = dict(taper="dpss", taper_opt={"NW": 4, "Kmax": 7}, polyremoval=0, output="pow", keeptapers=False, engine=eng)
+    ms = timed(lambda: keep.__setitem__("s", batched.mtmconvol(x, 1024., 512, 256, **kw)[0]))
+    spec = keep["s"]
+    alg = 4 * N * C + 4 * spec.shape[1] * spec.shape[3] * C                       # SURVEY 8d: 16,809,984 B / trial
+    out["cfg3_mtmconvol"] = dict(
+        workload="mtmconvol K=7 DPSS, nperseg 512, hop 256, pow, taper mean; 100 trials x 128 ch x 16384 smp per GPU",
+        scaling="weak", trials_per_gpu=T, ms=ms, value=T * world / ms * 1e3, unit="trials/s",
+        algorithmic_bytes_per_trial=alg, achieved_gbs=alg * T / ms / 1e6, frac_of_hbm_peak=alg * T / ms / 1e6 / hbm,
+        bound="hbm")
+    del x, spec
+    keep.clear()
+    # ---- cfg-5: wavelet / superlet, 64 ch x 8192 smp, 50 scales, pow, toi='all'; 16 trials per GPU in the timed region
+    T, N, C = 16, 8192, 64
+    x = torch.randn((T, N, C), device=dev)
+    foi = np.arange(1., 101., 2.)
+    wav = hm.Morlet(6)
+    alg = 4 * N * C * (1 + foi.size)                                              # SURVEY 8d: 106,954,752 B / trial
+    ms = timed(lambda: keep.__setitem__("w", batched.wavelet(x, 1000., wav.scale_from_period(1 / foi), wav,
+                                                             output="pow", engine=eng, trial_chunk=8)))
+    out["cfg5_wavelet"] = dict(
+        workload="wavelet Morlet(6), 50 scales (1..99 Hz), pow, toi='all'; 64 ch x 8192 smp, 16 trials per GPU timed "
+                 "(the 1000-trial job is this step repeated: trials are independent)",
+        scaling="weak", trials_per_gpu=T, ms=ms, value=T * world / ms * 1e3, unit="trials/s",
+        algorithmic_bytes_per_trial=alg, achieved_gbs=alg * T / ms / 1e6, frac_of_hbm_peak=alg * T / ms / 1e6 / hbm,
+        bound="hbm (FFT-throughput bound while every scale uses the full padded length)")
+    scales = 1.0 / (2 * np.pi * foi)
+    for adaptive in (False, True):
+        sc = scales[::-1].copy() if adaptive else scales          # FASLT wants scales high -> low
+        ms = timed(lambda: keep.__setitem__("s", batched.superlet(x, 1000., sc, order_max=10, order_min=1, c_1=3,
+                                                                  adaptive=adaptive, output="pow", engine=eng,
+                                                                  trial_chunk=8)), iters=2)
+        out["cfg5_superlet_" + ("faslt" if adaptive else "multiplicative")] = dict(
+            workload="superlet orders 1-10, c1=3, " + ("FASLT" if adaptive else "multiplicative") +
+                     ", 50 scales, pow; 64 ch x 8192 smp, 16 trials per GPU timed",
+            scaling="weak", trials_per_gpu=T, ms=ms, value=T * world / ms * 1e3, unit="trials/s",
+            algorithmic_bytes_per_trial=alg, achieved_gbs=alg * T / ms / 1e6,
+            frac_of_hbm_peak=alg * T / ms / 1e6 / hbm, bound="hbm")
+    del x
+    keep.clear()
+    # ---- cfg-4: granger, 500 trials x 128 ch x 4096 smp in TOTAL, sharded over the ranks (BASELINE: 8 B200)
+    T, N, C = 500, 4096, 128
+    lo, hi = (T * rank) // world, (T * (rank + 1)) // world
+    x = torch.randn((hi - lo, N, C), device=dev)
+    gk = dict(taper="dpss", taper_opt={"NW": 2, "Kmax": 3}, polyremoval=0, engine=eng)
+    ms = timed(lambda: keep.__setitem__("g", batched.granger(x, 200., reduce_group=group, **gk)), iters=2)
+    G, meta, _ = keep["g"]
+    csd_ms = timed(lambda: batched.cross_spectra_sum(x, 200., demean_taper=True, **gk), iters=2)
+    iters = int(meta["iterations"])
+    nF = N // 2 + 1
+    flop_iter = 6 * 8.0 * C ** 3 * nF                       # SURVEY 8d: ~6 complex C^3 GEMM-equivalents per frequency
+    fact_ms = ms - csd_ms
+    dg = dgemm_peak_tflops(dev)
+    out["cfg4_granger"] = dict(
+        workload=f"granger (K=3 DPSS, demean_taper), 500 trials x 128 ch x 4096 smp in total sharded over {world} "
+                 f"GPU(s): CSD stage + all-reduce of the CSD sum, regularisation, Wilson (frequency-slab sharded for "
+                 f"N > 1), Geweke-Granger",
+        scaling="strong", total_trials=T, ms=ms, value=T / ms * 1e3, unit="trials/s", csd_stage_ms=csd_ms,
+        factorisation_ms=fact_ms, wilson_iterations=iters, ms_per_iteration=fact_ms / max(1, iters),
+        converged=bool(meta["converged--bool"]), finite=bool(torch.isfinite(G).all()),
+        algorithmic_bytes_per_trial_csd_stage=4 * N * C + 8 * nF * C * C / T,
+        wilson_fp64_flop_per_iteration=flop_iter,
+        wilson_fp64_tflops=flop_iter * iters / (fact_ms * 1e-3) / 1e12,
+        fp64_peak_tflops_measured_dgemm=dg, frac_of_fp64_peak=flop_iter * iters / (fact_ms * 1e-3) / 1e12 / dg,
+        bound="fp64 pipe (factorisation) / tensor (CSD stage)")
+    del x, G
+    keep.clear()
+    if with_cpu and rank == 0:
+        cpu = cpu_config_samples()
+        for key, name in (("cfg3_mtmconvol", "cfg3"), ("cfg5_wavelet", "cfg5_wavelet"),
+                          ("cfg5_superlet_multiplicative", "cfg5_superlet"), ("cfg5_superlet_faslt", "cfg5_superlet_faslt"),
+                          ("cfg4_granger", "cfg4")):
+            out[key]["cpu_baseline"] = cpu.get(name)
+        c4 = cpu.get("cfg4") or {}
+        if "t_trial_s" in c4:
+            cores = os.cpu_count() or 1
+            it = out["cfg4_granger"]["wilson_iterations"]
+            job = 500 * c4["t_trial_s"] / cores + c4["t_cond_s"] + it * c4["t_wilson_1iter_s"]
+            out["cfg4_granger"]["cpu_baseline"]["job_model_s"] = job
+            out["cfg4_granger"]["cpu_baseline"]["job_model"] = (
+                f"MODEL: 500 trials x {c4['t_trial_s']:.2f} s / {cores} cores + 1 condition-number pass + {it} Wilson "
+                f"iterations x {c4['t_wilson_1iter_s']:.2f} s (single process, as the reference runs the averaged stage)")
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from syncopy_b200 import _lib, batched
-    from syncopy_b200 import hostmath as hm
     from syncopy_b200.engine import get_engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -289,108 +703,51 @@ def run_gpu_arm(args):
     x = host.to(dev)
 
     n_freq = N_SAMPLES // 2 + 1
-    tapers = eng.taper_table(w["taper"], N_SAMPLES, N_SAMPLES, w["taper_opt"])
-    scale = hm.mtmfft_scale(N_SAMPLES, N_SAMPLES)
     total_trials = N_TRIALS * world
     group = dist.group.WORLD if world > 1 else None
-    # default path: tcgen05 contraction writing upper tiles into per-frequency-slab slot buffers (peer stores over
-    # NVLink for N > 1), then per-slab sum + normalisation; --csd-impl 1/3 select the older paths for comparison
-    mode = {0: "tiles", 2: "tiles", 1: "simt", 3: "planar"}[args.csd_impl]
-    if mode == "tiles" and not eng.csd_planar_supported(N_CHAN):
-        mode = "simt"
-    # one rank: the contraction's epilogue normalises and mirrors itself (K2 + K3 in one kernel, no CSD in memory)
-    fused = mode == "tiles" and world == 1 and args.csd_impl == 0
-    if mode == "tiles":
-        from syncopy_b200.distributed import get_tile_exchange
-        ex = get_tile_exchange(eng, n_freq, N_CHAN, group)
-        nf_local = ex.nf_local
-    else:
-        nf_local = n_freq
-    if mode in ("tiles", "planar"):   # planar re|im rows: operand layout of the tcgen05 cross-spectral kernel
-        spectra = torch.empty((n_freq, N_TRIALS * K, 2, N_CHAN), dtype=torch.float32, device=dev)
-    else:
-        spectra = torch.empty((n_freq, N_TRIALS * K, N_CHAN), dtype=torch.complex64, device=dev)
-    csd_sum = None if mode == "tiles" else torch.empty((n_freq, N_CHAN, N_CHAN), dtype=torch.complex64, device=dev)
-    coh = torch.empty((1, nf_local, N_CHAN, N_CHAN), dtype=torch.float32, device=dev)
-    coh_host = torch.empty(coh.shape, dtype=torch.float32).pin_memory()
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
-
-    def step(marks=None):
-        if marks is not None:
-            marks[0].record()
-        eng.mtmfft(x, tapers, N_SAMPLES, scale, polyremoval=0, output="fourier" if mode == "simt" else "fourier_planar",
-                   keeptapers=True, out=spectra, freq_major=True)
-        if marks is not None:
-            marks[1].record()
-        if fused:
-            eng.csd_coherence_planar(spectra, output="abs", out=coh[0])
-            if marks is not None:
-                for m in marks[2:]:
-                    m.record()
-            return
-        if mode == "tiles":
-            ex.accumulate(spectra, alpha=1.0 / K, beta=0.0)
-        elif mode == "planar":
-            eng.csd_accumulate_planar(spectra, acc=csd_sum, alpha=1.0 / K, beta=0.0)
-        else:
-            eng.csd_accumulate(spectra, acc=csd_sum, alpha=1.0 / K, beta=0.0, impl=1)
-        if marks is not None:
-            marks[2].record()
-        if mode == "tiles":
-            ex.barrier(N_TRIALS, n_total=total_trials)       # counter all-reduce: every rank's tiles have landed
-            if marks is not None:
-                marks[3].record()
-            ex.normalize(total_trials, output="abs", out=coh[0])   # per-slab sum over ranks + normalisation
-            if marks is not None:
-                marks[4].record()
-            return
-        if world > 1:
-            dist.all_reduce(torch.view_as_real(csd_sum))
-        if marks is not None:
-            marks[3].record()
-        eng.csd_normalize(csd_sum[None], output="abs", pre_scale=1.0 / total_trials, out=coh)
-        if marks is not None:
-            marks[4].record()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident throughput ------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    # ---- device-resident throughput (weak scaling: 200 trials per rank) ------------------------------
+    stepper = Cfg2Step(eng, x, args, group, world, rank, total_trials)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    marks = [[ev() for _ in range(5)] for _ in range(args.steps)]
-    launches0 = _lib.launch_count()
-    barrier()
-    t_start, t_end = ev(), ev()
-    t_start.record()
-    for i in range(args.steps):
-        step(marks[i])
-    t_end.record()
-    barrier()
-    launches = _lib.launch_count() - launches0
-    elapsed_ms = t_start.elapsed_time(t_end)
-    seg = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(4)] for m in marks])   # ms: fft, csd, allreduce, norm
-    if world > 1:
-        tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tmax.item())
+    warm = max(args.warmup, 3)
+    elapsed_ms, seg = timed_steps(stepper, args.steps, warm, barrier, dev, world)
     ms_per_step = elapsed_ms / args.steps
     value = total_trials * args.steps / (elapsed_ms * 1e-3)
+    parity = parity_block(stepper, hnp, args, world, rank, dev)
+
+    # ---- strong scaling (N > 1): 200 trials in TOTAL over the ranks --------------------------------------
+    strong = None
+    if world > 1:
+        lo, hi = (N_TRIALS * rank) // world, (N_TRIALS * (rank + 1)) // world
+        # rank r takes trials [lo, hi) of ITS OWN shard as stand-ins (same shapes, same arithmetic)
+        s_step = Cfg2Step(eng, x[: hi - lo], args, group, world, rank, N_TRIALS)
+        s_ms, s_seg = timed_steps(s_step, args.steps, 3, barrier, dev, world)
+        sf, sc_, sb, sn = s_seg.mean(axis=0)
+        strong = {"total_trials": N_TRIALS, "trials_per_gpu": hi - lo, "ms_per_step": s_ms / args.steps,
+                  "value": N_TRIALS * args.steps / (s_ms * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "kernels_ms": {"mtmfft (K1)": float(sf), "csd (K2)": float(sc_), "barrier": float(sb),
+                                 "normalize (K3)": float(sn)},
+                  "note": "fixed total work: the per-rank kernels shrink with N while the exchange barrier and the "
+                          "per-slab normalisation do not -- SURVEY 8e's caveat"}
+        del s_step
 
     # ---- end to end through the public API (pinned host in, pinned host out) ---------------------
+    coh_host = torch.empty(stepper.coh.shape, dtype=torch.float32).pin_memory()
+
     def e2e_step():
         c, _ = batched.coherence(host, FS, taper=w["taper"], taper_opt=w["taper_opt"], polyremoval=0,
                                  output="abs", engine=eng, impl={0: 0, 2: 0, 1: 1, 3: 1}[args.csd_impl],
                                  reduce_group=group, out_host=coh_host, gather=False)
         return c
 
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     for _ in range(2):
         e2e_step()
     barrier()
@@ -409,13 +766,18 @@ def run_gpu_arm(args):
     e2e_value = total_trials * e2e_steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
-    # quick self-check of the e2e result against the device-resident one
-    assert torch.isfinite(coh).all()
-    dmax = (coh_host.to(dev) - coh).abs().max().item()
+    # the e2e result must agree with the device-resident one
+    assert torch.isfinite(stepper.coh).all()
+    dmax = (coh_host.to(dev) - stepper.coh).abs().max().item()
     assert dmax < 1e-5, f"e2e result deviates from device-resident result ({dmax})"
 
+    peaks = load_peaks()
+    configs = None
+    if not args.no_configs:
+        configs = configs_block(eng, peaks, world, rank, group, with_cpu=(world == 1 and not args.no_cpu_baseline))
+
     if rank == 0:
-        peaks = load_peaks()
+        mode, fused, nf_local = stepper.mode, stepper.fused, stepper.nf_local
         fft_ms, csd_ms, ar_ms, norm_ms = seg.mean(axis=0)
         in_bytes = N_TRIALS * N_SAMPLES * N_CHAN * 4
         spec_bytes = n_freq * N_TRIALS * K * N_CHAN * 8
@@ -435,10 +797,15 @@ def run_gpu_arm(args):
             "share_of_step": float(csd_ms / ms_per_step),
         }
         k1_gbs = (in_bytes + spec_bytes) / (fft_ms * 1e-3) / 1e9
+        k1_kernel = "mtm_tma_kernel" if K == 1 else "mtm_dif_kernel"
         roofline_k1 = {
-            "kernel": "tapered FFT (K1, in-place radix-16 DIF in shared memory)", "bound": "hbm", "achieved": k1_gbs,
+            "kernel": "tapered FFT (K1, %s)" % ("persistent TMA-fed in-place radix-16 DIF, packed FP32" if K == 1 else
+                                                "in-place radix-16 DIF in shared memory"),
+            "bound": "hbm", "achieved": k1_gbs,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k1_gbs / peaks["hbm_gbs"],
-            "traffic": load_traffic("mtm_dif_kernel", args.taper),
+            "traffic": load_traffic(k1_kernel, args.taper),
+            "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this build's kernel; a constant, "
+                              "not measured by this run)",
             "peak_source": f"{peaks['source']} HBM copy bandwidth",
             "algorithmic": f"4*N*C in + 8*K*nFreq*C out per trial = {(in_bytes + spec_bytes) / N_TRIALS / 1e6:.3f} MB, "
                            f"x{N_TRIALS} trials/launch",
@@ -457,7 +824,7 @@ def run_gpu_arm(args):
                          "bytes_gbs": (spec_bytes + csd_bytes * tile_frac) / (csd_ms * 1e-3) / 1e9},
             ("barrier" if mode == "tiles" else "allreduce"): {"ms": float(ar_ms)},
             "normalize (K3)": {"ms": float(norm_ms), "bound": "hbm",
-                               "achieved_gbs": k3_bytes / (norm_ms * 1e-3) / 1e9},
+                               "achieved_gbs": k3_bytes / max(norm_ms, 1e-9) / 1e6},
         }
         if fused:       # K2's epilogue normalises: one kernel, coherence written once (4 B per element)
             del kernels["barrier"], kernels["normalize (K3)"]
@@ -470,23 +837,42 @@ def run_gpu_arm(args):
         }
         cpu_info = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_info, _ = cpu_reference_sample(args.taper)
+            ref = CpuReference(args.taper)
+            ref.sample(1)
+            cpu_info = ref.info()
+            cpu_info["full_job_model"] = ref.job_model()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-                    "d2h_bytes_per_step": coh.numel() * 4, "steps": e2e_steps,
+                    "d2h_bytes_per_step": stepper.coh.numel() * 4, "steps": e2e_steps,
                     "api": "syncopy_b200.batched.coherence(pinned host trials) -> pinned host coherence"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(_count_launches_per_step(stepper) * args.steps),
+            "parity": parity,
             "roofline": roofline, "kernels": kernels, "hbm_pipeline": hbm_pipeline,
             "cpu_baseline": cpu_info, "clocks": clocks,
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if configs is not None:
+            line["configs"] = configs
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _count_launches_per_step(stepper):
+    """libspyb200 kernels launched by one step (counted on a fresh step, not assumed)"""
+    import torch
+    from syncopy_b200 import _lib
+    torch.cuda.synchronize(stepper.eng.tdev)
+    n0 = _lib.launch_count()
+    stepper.step()
+    torch.cuda.synchronize(stepper.eng.tdev)
+    return _lib.launch_count() - n0
 
 
 _REAL_STDOUT = None
@@ -518,6 +904,7 @@ def main():
     ap.add_argument("--csd-impl", dest="csd_impl", type=int, default=0,
                     help="0 tcgen05 + tile slots (default), 1 CUDA-core kernel + all-reduce, 3 tcgen05 full CSD + all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg-3/4/5 block")
     args = ap.parse_args()
     if args.impl == "reference":
         _quiet_stdout()

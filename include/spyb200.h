@@ -194,6 +194,48 @@ int spyb_gather_rows(const float* src, int n_trials, long long src_trial_stride,
 int spyb_scale(float* x, long long n, float s, void* stream);
 
 /*
+ * acc[e] = beta*acc[e] + alpha * sum_{b < n_trials} src[b*trial_stride + e], e < n_elems (float32; complex64 data counts
+ * two floats per element).  Replaces the runtime's trial accumulation `target[()] += res` and the final
+ * `target[()] /= numTrials` of syncopy/shared/computational_routine.py:1025,1030-1032 for a batch of trials.
+ * n_elems, trial_stride multiples of 4, pointers 16-byte aligned.
+ */
+int spyb_sum_trials(const float* src, int n_trials, long long trial_stride, long long n_elems, float alpha, float beta,
+                    float* acc, void* stream);
+
+/*
+ * Jackknife over trials (syncopy/statistics/jackknifing.py:14-184) -- element-wise pieces on float32 words
+ * (a complex64 array counts two words per element):
+ *   spyb_axpby            out = a*x + b*y (y may be NULL): leave-one-out replicate (T*avg - x_k)/(T-1) (:80-85) and
+ *                         bias = (T-1)*(jack_avg - direct) (:160)
+ *   spyb_sqdev_accumulate var[e] += |avg[e] - x[e]|^2 over n_elem elements, real or complex input (:164-170)
+ */
+int spyb_axpby(const float* x, const float* y, float a, float b, float* out, long long n, void* stream);
+int spyb_sqdev_accumulate(const float* avg, const float* x, float* var, long long n_elem, int is_complex, void* stream);
+
+/*
+ * Pairwise phase consistency (syncopy/connectivity/ST_compRoutines.py:158-233 `ppc_column_cF` and the pair loop
+ * of connectivity_analysis.py:624-667): the average of cos(angle(z_j conj z_k)) over all trial pairs j < k equals
+ * (|sum_k z_k/|z_k||^2 - T) / (T (T - 1)), so one pass over the T single-trial cross spectra replaces T(T-1)/2 pair
+ * evaluations.  spyb_unit_accumulate adds the unit vectors of one trial's cross spectra (complex64, n elements;
+ * `first` != 0 initialises acc), spyb_ppc_finish turns the sums into the float32 PPC.
+ */
+int spyb_unit_accumulate(const void* z, void* acc, long long n, int first, void* stream);
+int spyb_ppc_finish(const void* acc, float* out, long long n, int n_trials, void* stream);
+
+/*
+ * Cross-covariance of one trial (syncopy/connectivity/ST_compRoutines.py:465-584): the C^2 `fftconvolve(x_i,
+ * x_j[::-1], 'same')` calls become one forward spectrum per channel (spyb_mtmfft, unit taper, n_dft >= 2 n - 1), kernel
+ * spectra of the reversed channels (spyb_xcov_kernel_spectra; xspec [chan][n_dft/2+1] complex64 ->
+ * kern [chan][n_dft] complex64, circular result advanced by `shift` samples), the batched inverse transforms of
+ * spyb_cwt (real output, n_time = 2 n_lags + 1, shift = n - 1 - n_lags) and spyb_xcov_finish, which picks the lags
+ * (incl. the one-sample asymmetry of 'same' for even n, :555-566), divides by the overlap n - s and optionally by the
+ * channel standard deviations (:569-572).  out [n_lags][C][C] float32.
+ */
+int spyb_xcov_kernel_spectra(const void* xspec, int n_chan, int n_dft, int n_samples, int shift, void* kern, void* stream);
+int spyb_xcov_finish(const float* corr, const void* xspec, int n_chan, int n_samples, int n_lags, int n_dft, int norm,
+                     float* out, void* stream);
+
+/*
  * Granger causality path (float64 / complex128 like the reference, AV_compRoutines.py:395).  These three calls
  * synchronise `stream` internally: the regularisation ladder and Wilson's iteration are data dependent.
  * `work` is caller-owned device scratch of at least spyb_*_workspace_bytes().  `_host` pointers are host memory.

@@ -51,6 +51,13 @@ PROTOTYPES = {
     "spyb_transpose": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "spyb_gather_rows": (_i, [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp]),
     "spyb_scale": (_i, [_vp, _ll, _f, _vp]),
+    "spyb_sum_trials": (_i, [_vp, _i, _ll, _ll, _f, _f, _vp, _vp]),
+    "spyb_axpby": (_i, [_vp, _vp, _f, _f, _vp, _ll, _vp]),
+    "spyb_sqdev_accumulate": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "spyb_unit_accumulate": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "spyb_ppc_finish": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "spyb_xcov_kernel_spectra": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "spyb_xcov_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "spyb_regularize_workspace_bytes": (_ll, [_i, _i]),
     "spyb_regularize_csd": (_i, [_vp, _i, _i, _d, _d, _i, _vp, _dp, _dp, _vp, _ll, _vp]),
     "spyb_wilson_workspace_bytes": (_ll, [_i, _i]),

@@ -58,10 +58,27 @@ def mtmfft(trials, samplerate, nSamples=None, taper="hann", taper_opt=None, deme
                       freq_idx=fidx, output=output, keeptapers=keeptapers)
     if not keeptrials:
         # runtime's trial mean: sum of the per-trial results / nTrials (computational_routine.py:1022-1032)
-        spec = spec.sum(dim=0, keepdim=True) / B
+        spec = eng.sum_trials(spec, alpha=1.0 / B)[None]
     if to_host:
         spec = spec.cpu().numpy()
     return spec, freqs
+
+
+def mtmconvol_frames(n_sig, nperseg, noverlap, boundary="zeros", padded=True):
+    """(first frame start, number of frames kept) of `mtmconvol` for a trial of n_sig samples
+    (syncopy/specest/mtmconvol.py:120-126,150; stft.py:101-127)."""
+    hop = nperseg - noverlap
+    n_keep = int(np.ceil(n_sig / hop))
+    ext = n_sig
+    if boundary is not None:
+        frame_start0 = -(nperseg // 2)
+        ext += 2 * (nperseg // 2)
+    else:
+        frame_start0 = 0
+        n_keep -= nperseg
+    if padded:
+        ext += (-(ext - nperseg) % hop) % nperseg
+    return frame_start0, max(0, min(n_keep, (ext - noverlap) // hop))
 
 
 def mtmconvol(trials, samplerate, nperseg, noverlap, taper="hann", taper_opt=None, boundary="zeros",
@@ -78,17 +95,7 @@ def mtmconvol(trials, samplerate, nperseg, noverlap, taper="hann", taper_opt=Non
     hop = nperseg - noverlap
     freqs, fidx = _freq_selection(nperseg, samplerate, foi)
     tapers = eng.taper_table(taper, nperseg, nperseg, taper_opt, periodic_dpss=True)
-    n_keep = int(np.ceil(n_sig / hop))
-    ext = n_sig
-    if boundary is not None:
-        frame_start0 = -(nperseg // 2)
-        ext += 2 * (nperseg // 2)
-    else:
-        frame_start0 = 0
-        n_keep -= nperseg
-    if padded:
-        ext += (-(ext - nperseg) % hop) % nperseg
-    n_frames = max(0, min(n_keep, (ext - noverlap) // hop))
+    frame_start0, n_frames = mtmconvol_frames(n_sig, nperseg, noverlap, boundary, padded)
     spec = eng.mtmconvol(x, tapers, nperseg, hop, frame_start0, n_frames, hm.stft_scale(nperseg),
                          polyremoval=hm.polyremoval_code(polyremoval), freq_idx=fidx, output=output,
                          keeptapers=keeptapers)
@@ -284,8 +291,9 @@ def granger(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_o
     """
     `connectivityanalysis(method='granger')` compute chain: CrossSpectra(keeptrials=False, demean_taper=True)
     followed by GrangerCausality (syncopy/connectivity/connectivity_analysis.py:576,864; AV_compRoutines.py:292-412).
-    With `reduce_group`, `trials` is this rank's shard: the CSD sum is all-reduced and every rank then runs the
-    (replicated) factorisation.  Returns (granger [1, nFreq, C, C] float32, metadata dict, freqs).
+    With `reduce_group`, `trials` is this rank's shard: the CSD sum is all-reduced, every rank regularises the
+    average, the Wilson factorisation is sharded by frequency slab over the ranks (`spyb_wilson_sharded`) and the
+    Granger slabs are gathered.  Returns (granger [1, nFreq, C, C] float32, metadata dict, freqs).
     """
     eng = engine or get_engine()
     res = cross_spectra_sum(trials, samplerate, nSamples, foi, taper, taper_opt, True, polyremoval,

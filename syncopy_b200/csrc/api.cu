@@ -207,6 +207,36 @@ int spyb_scale(float* x, long long n, float s, void* stream) {
     return scale_inplace(x, n, s, static_cast<cudaStream_t>(stream));
 }
 
+int spyb_sum_trials(const float* src, int n_trials, long long trial_stride, long long n_elems, float alpha, float beta,
+                    float* acc, void* stream) {
+    return sum_trials(src, n_trials, trial_stride, n_elems, alpha, beta, acc, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_axpby(const float* x, const float* y, float a, float b, float* out, long long n, void* stream) {
+    return axpby(x, y, a, b, out, n, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_sqdev_accumulate(const float* avg, const float* x, float* var, long long n_elem, int is_complex, void* stream) {
+    return sqdev_accumulate(avg, x, var, n_elem, is_complex, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_unit_accumulate(const void* z, void* acc, long long n, int first, void* stream) {
+    return unit_accumulate(z, acc, n, first, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_ppc_finish(const void* acc, float* out, long long n, int n_trials, void* stream) {
+    return ppc_finish(acc, out, n, n_trials, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_xcov_kernel_spectra(const void* xspec, int n_chan, int n_dft, int n_samples, int shift, void* kern, void* stream) {
+    return xcov_kernel_spectra(xspec, n_chan, n_dft, n_samples, shift, kern, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_xcov_finish(const float* corr, const void* xspec, int n_chan, int n_samples, int n_lags, int n_dft, int norm,
+                     float* out, void* stream) {
+    return xcov_finish(corr, xspec, n_chan, n_samples, n_lags, n_dft, norm, out, static_cast<cudaStream_t>(stream));
+}
+
 long long spyb_regularize_workspace_bytes(int n_freq, int n_chan) {
     return regularize_workspace_bytes(n_freq, n_chan);
 }

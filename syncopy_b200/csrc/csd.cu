@@ -453,4 +453,40 @@ int scale_inplace(float* x, long long n, float s, cudaStream_t stream) {
     return 0;
 }
 
+// acc[e] = beta * acc[e] + alpha * sum_b src[b][e]: the runtime's `target[()] += res` over a batch of trials and the
+// final `/= numTrials` (computational_routine.py:1025,1030-1032).  Trials are added in index order per element.
+__global__ void sum_trials_kernel(const float4* __restrict__ src, int n_trials, long long stride4, long long n4,
+                                  float alpha, float beta, float4* __restrict__ acc) {
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = i0; i < n4; i += step) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < n_trials; ++b) {
+            const float4 v = __ldg(src + (long long)b * stride4 + i);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        float4 o = make_float4(alpha * s.x, alpha * s.y, alpha * s.z, alpha * s.w);
+        if (beta != 0.f) {
+            const float4 a = acc[i];
+            o.x += beta * a.x; o.y += beta * a.y; o.z += beta * a.z; o.w += beta * a.w;
+        }
+        acc[i] = o;
+    }
+}
+
+int sum_trials(const float* src, int n_trials, long long trial_stride, long long n_elems, float alpha, float beta,
+               float* acc, cudaStream_t stream) {
+    if (n_elems <= 0) return 0;
+    if (n_elems % 4 || trial_stride % 4 || reinterpret_cast<uintptr_t>(src) % 16 || reinterpret_cast<uintptr_t>(acc) % 16)
+        return fail("sum_trials: element count, trial stride and pointers must be multiples of 4 floats / 16 bytes");
+    const long long n4 = n_elems / 4;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sum_trials_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), n_trials, trial_stride / 4, n4,
+                                                            alpha, beta, reinterpret_cast<float4*>(acc));
+    SPYB_LAUNCH_CHECK("sum_trials_kernel");
+    count_launch();
+    return 0;
+}
+
 }  // namespace spyb

@@ -767,11 +767,8 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2) +
                         2 * 128 * sizeof(float);
 
-    static bool configured = false;
-    if (!configured) {
-        SPYB_CUDA(cudaFuncSetAttribute(csd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+    // per device / context attribute: set on every launch (several engines may live in one process)
+    SPYB_CUDA(cudaFuncSetAttribute(csd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int dev = 0, n_sm = 148;
     SPYB_CUDA(cudaGetDevice(&dev));
     SPYB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));

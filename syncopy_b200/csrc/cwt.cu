@@ -190,11 +190,8 @@ static int launch_cwt(const CwtArgs& a, bool need_acc, cudaStream_t stream) {
     const size_t smem = (size_t)fft_padded_len(N) * P * sizeof(float2) +
                         (need_acc ? (size_t)a.n_time * P * sizeof(float2) : 0);
     if (smem > 227 * 1024) return fail("cwt: transform does not fit shared memory (%zu bytes)", smem);
-    static size_t configured = 0;   // per template instantiation
-    if (smem > configured) {
-        SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    // per device / context attribute: set on every launch (several engines may live in one process)
+    SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.n_scales > 65535 || a.n_trials > 65535) return fail("cwt: too many scales / trials per launch");
     dim3 grid((a.n_chan + P - 1) / P, a.n_scales, a.n_trials);
     kern<<<grid, THREADS, smem, stream>>>(a);

@@ -286,11 +286,8 @@ static int launch_one(const MtmArgs& a, cudaStream_t stream) {
     auto kern = mtm_kernel<LOG2N, P, BLUE, THREADS, MINB>;
     const size_t smem = (size_t)G * fft_padded_len(N) * P * sizeof(float2) +
                         (size_t)(THREADS / 32 + 1) * P * 4 * sizeof(float);
-    static bool configured = false;   // per template instantiation
-    if (!configured) {
-        SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per device / context attribute: set on every launch (several engines may live in one process)
+    SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int chan_tiles = (a.n_chan + 2 * P - 1) / (2 * P);
     const int frame_blocks = (a.n_frames + G - 1) / G;
     if (frame_blocks > 65535 || a.n_trials > 65535)

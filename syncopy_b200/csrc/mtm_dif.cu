@@ -413,11 +413,8 @@ int launch_dif(const MtmArgs& a_in, cudaStream_t stream) {
         }
     }
     auto kern = a.acc_smem ? mtm_dif_kernel<LOG2N, P, THREADS, MINB, true> : mtm_dif_kernel<LOG2N, P, THREADS, MINB, false>;
-    static bool configured[2] = {false, false};   // per template instantiation
-    if (!configured[a.acc_smem]) {
-        SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        configured[a.acc_smem] = true;
-    }
+    // per device / context attribute: set on every launch (several engines may live in one process)
+    SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     const int chan_tiles = (a.n_chan + 2 * P - 1) / (2 * P);
     if (a.n_frames > 65535 || a.n_trials > 65535)
         return fail("mtm launch: too many frames (%d) or trials (%d) for one launch", a.n_frames, a.n_trials);

@@ -38,8 +38,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
-#include <map>
-#include <mutex>
 
 #include "common.cuh"
 #include "mtm_args.cuh"
@@ -559,17 +557,8 @@ EncodeTiledFn get_encode_fn() {
 template <bool PLANAR>
 int launch(const CUtensorMap& tmap, const TmaArgs& ta, int grid, cudaStream_t stream) {
     auto kern = mtm_tma_kernel<PLANAR>;
-    static std::mutex mu;
-    static std::map<int, bool> configured;      // per device
-    int dev = 0;
-    SPYB_CUDA(cudaGetDevice(&dev));
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!configured[dev]) {
-            SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            configured[dev] = true;
-        }
-    }
+    // per device / context attribute: set on every launch (several engines may live in one process)
+    SPYB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     kern<<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, ta);
     SPYB_LAUNCH_CHECK("mtm_tma_kernel");
     count_launch();

@@ -81,6 +81,17 @@ int gather_rows(const float* src, int n_trials, long long src_trial_stride, cons
 int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind, void* out,
                   cudaStream_t stream);
 int scale_inplace(float* x, long long n, float s, cudaStream_t stream);
+int sum_trials(const float* src, int n_trials, long long trial_stride, long long n_elems, float alpha, float beta,
+               float* acc, cudaStream_t stream);
+
+// Jackknife / PPC / cross-covariance helpers (stats.cu)
+int axpby(const float* x, const float* y, float a, float b, float* out, long long n, cudaStream_t st);
+int sqdev_accumulate(const float* avg, const float* x, float* var, long long n_elem, int is_complex, cudaStream_t st);
+int unit_accumulate(const void* z, void* acc, long long n, int first, cudaStream_t st);
+int ppc_finish(const void* acc, float* out, long long n, int n_trials, cudaStream_t st);
+int xcov_kernel_spectra(const void* xspec, int n_chan, int L, int n, int shift, void* kern, cudaStream_t st);
+int xcov_finish(const float* corr, const void* xspec, int n_chan, int n, int n_lags, int L, int norm, float* out,
+                cudaStream_t st);
 
 // Granger path: regularisation, Wilson spectral factorisation, Geweke-Granger formula (wilson.cu); FP64
 long long regularize_workspace_bytes(int n_freq, int n_chan);

@@ -943,13 +943,10 @@ int fft_axis0(zd* a, zd* b, const zd* tw, int len, long long E, const FftPlanZ& 
 size_t fact_smem(int n) { return ((size_t)n * PLD + (size_t)NB * 2 * n) * sizeof(zd); }
 
 int ensure_fact_smem() {
-    static bool done = false;
-    if (!done) {
-        const int mx = (int)fact_smem(MAX_CHAN);
-        SPYB_CUDA(cudaFuncSetAttribute(zpotrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        SPYB_CUDA(cudaFuncSetAttribute(zgesv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        done = true;
-    }
+    // per device / context attribute: set on every call (several engines may live in one process)
+    const int mx = (int)fact_smem(MAX_CHAN);
+    SPYB_CUDA(cudaFuncSetAttribute(zpotrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    SPYB_CUDA(cudaFuncSetAttribute(zgesv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     return 0;
 }
 
@@ -1138,6 +1135,24 @@ int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double r
     const int m_lo = f_lo > 1 ? f_lo : 1, m_hi = f_hi < nf - 1 ? f_hi : nf - 1;    // mirrored rows: len - f, f in [m_lo, m_hi)
     const int mrow0 = len - m_hi + 1, mrows = m_hi > m_lo ? m_hi - m_lo : 0;
 
+    // A numerical failure (non-positive-definite CSD, singular psi: numpy.linalg.LinAlgError in the reference) is seen
+    // only by the rank that owns the frequency.  All ranks must take the same decision, or the ones that carry on
+    // would wait in the next collective for ever: the flag is max-reduced through the exchange callback.
+    auto agree_failure = [&](int local_fail) -> int {
+        if (!exchange) return local_fail;
+        double v = local_fail ? 1.0 : 0.0;
+        double* flag = reinterpret_cast<double*>(w.err_bits + 1);
+        if (cudaMemcpyAsync(flag, &v, sizeof(v), cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+        if (exchange(exchange_ctx, 1, flag, 8, 1)) return 1;
+        if (cudaMemcpyAsync(&v, flag, sizeof(v), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+        if (v != 0.0 && !local_fail)
+            fail("wilson_sf: another rank found a non-positive-definite or singular matrix in its frequency slab "
+                 "(numpy.linalg.LinAlgError in the reference)");
+        return v != 0.0 ? 1 : 0;
+    };
+
     SPYB_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int) * ((size_t)nf + 8), st));
     twiddle_kernel<<<(len + 255) / 256, 256, 0, st>>>(w.tw, len);
     SPYB_LAUNCH_CHECK("twiddle_kernel"); count_launch();
@@ -1152,7 +1167,7 @@ int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double r
     if (run_potrf(w.G0, 0, w.L0, 0, n, 1, w.info + nf, st)) return 1;
     // U = chol(CSD)                                         (wilson_sf.py:76)
     if (nfl > 0 && run_potrf(S + so, n2, w.Lchol + so, n2, n, nfl, w.info + f_lo, st)) return 1;
-    if (check_info(w.info, nf + 1, "wilson_sf (Cholesky of the CSD)", st)) return 1;
+    if (agree_failure(check_info(w.info, nf + 1, "wilson_sf (Cholesky of the CSD)", st))) return 1;
     psi_init_kernel<<<dim3(nb2, nfl > 0 ? nfl : 1), 256, 0, st>>>(w.L0, n, w.psi0A, nfl > 0 ? w.psiA : w.tmp0 - so, f_lo);
     SPYB_LAUNCH_CHECK("psi_init_kernel"); count_launch();
 
@@ -1209,7 +1224,7 @@ int wilson_sf(const void* csd_c128, int n_freq, int n_chan, int n_iter, double r
         memcpy(&err, &bits, sizeof(err));
         if (err < rtol) { converged = true; ++it; break; }
     }
-    if (nfl > 0 && check_info(w.info + f_lo, nfl, "wilson_sf (inverse of psi)", st)) return 1;
+    if (agree_failure(nfl > 0 ? check_info(w.info + f_lo, nfl, "wilson_sf (inverse of psi)", st) : 0)) return 1;
     // Sigma = psi0 psi0^T, H = psi psi0^-1                   (wilson_sf.py:114-118)
     if (run_gemm<1, 0>(psi0, 0, psi0, 0, w.tmp0, 0, nullptr, 0, nullptr, n, 1, false, st)) return 1;
     real_part_kernel<<<nb2, 256, 0, st>>>(w.tmp0, Sigma_out, n2);

@@ -6,11 +6,20 @@ one GPU; trial data and results live in caller-provided or freshly allocated
 PyTorch CUDA tensors that are handed to libspyb200 as raw device pointers.
 Everything is enqueued on torch's current stream of the device.
 """
+import functools
+import threading
+from collections import OrderedDict
+
 import numpy as np
 import torch
 
 from . import _lib
 from . import hostmath as hm
+
+# bounds of the per-engine device-side caches (entries): taper tables / index lists, convolution plans
+MAX_TABLES = 64
+MAX_PLANS = 8
+MAX_LAUNCH_DIM = 65535                      # CUDA grid.y / grid.z limit of one launch
 
 _CDTYPE = {True: torch.complex64, False: torch.float32}
 
@@ -28,6 +37,23 @@ def _trial_layout(x):
     return x.stride(0) if B > 1 else N * Cn
 
 
+def _on_own_device(cls):
+    """Run every public method with the engine's device current: the library launches on the current device."""
+    def wrap(fn):
+        @functools.wraps(fn)
+        def inner(self, *a, **kw):
+            if torch.cuda.current_device() == self.device:
+                return fn(self, *a, **kw)
+            with torch.cuda.device(self.device):
+                return fn(self, *a, **kw)
+        return inner
+    for name, attr in list(vars(cls).items()):
+        if callable(attr) and not name.startswith("_"):
+            setattr(cls, name, wrap(attr))
+    return cls
+
+
+@_on_own_device
 class Engine:
     def __init__(self, device=0):
         if not torch.cuda.is_available():
@@ -35,7 +61,10 @@ class Engine:
         self.device = int(device)
         self.lib = _lib.init(self.device)
         self.tdev = torch.device("cuda", self.device)
-        self._tables = {}
+        self._tables = {}                 # grow-only scratch buffers (few, reused)
+        self._lru = OrderedDict()         # taper tables, index lists: bounded, least recently used out first
+        self._plans = OrderedDict()       # convolution plans (tens of MB each): bounded
+        self._lock = threading.RLock()    # the process-wide engine is shared by worker threads
 
     # ------------------------------------------------------------------ utilities
     def stream(self):
@@ -51,33 +80,45 @@ class Engine:
         a = np.ascontiguousarray(arr)
         return torch.from_numpy(a).to(device=self.tdev, dtype=dtype, non_blocking=False).contiguous()
 
+    def _cached(self, cache, limit, key, make):
+        with self._lock:
+            if key in cache:
+                cache.move_to_end(key)
+                return cache[key]
+        val = make()
+        with self._lock:
+            cache[key] = val
+            cache.move_to_end(key)
+            while len(cache) > limit:
+                cache.popitem(last=False)     # tensors still referenced by a caller stay alive until released
+        return val
+
     def taper_table(self, taper, n_window, n_norm, taper_opt=None, periodic_dpss=False):
         key = ("taper", taper, int(n_window), int(n_norm), periodic_dpss,
                tuple(sorted((taper_opt or {}).items())))
-        if key not in self._tables:
-            tab = hm.normalized_tapers(taper, n_window, n_norm, taper_opt, periodic_dpss)
-            self._tables[key] = self.to_device(tab.astype(np.float32))
-        return self._tables[key]
+        return self._cached(self._lru, MAX_TABLES, key, lambda: self.to_device(
+            hm.normalized_tapers(taper, n_window, n_norm, taper_opt, periodic_dpss).astype(np.float32)))
 
     def scratch(self, name, shape, dtype):
         """Grow-only, reused device scratch tensor (e.g. the spectra handed from K1 to K2)."""
         n = int(np.prod(shape))
         key = ("scratch", name, dtype)
-        buf = self._tables.get(key)
-        if buf is None or buf.numel() < n:
-            self._tables[key] = None
-            buf = torch.empty(n, dtype=dtype, device=self.tdev)
-            self._tables[key] = buf
+        with self._lock:
+            buf = self._tables.get(key)
+            if buf is None or buf.numel() < n:
+                self._tables[key] = None
+                buf = torch.empty(n, dtype=dtype, device=self.tdev)
+                self._tables[key] = buf
         return buf[:n].view(shape)
 
-    def index_table(self, idx):
+    def index_table(self, idx, cache=True):
+        """int32 index list on the device; `cache=False` for per-call lists (gather tables of single trials)."""
         if idx is None:
             return None
         idx = np.ascontiguousarray(idx, dtype=np.int32)
-        key = ("idx", idx.tobytes())
-        if key not in self._tables:
-            self._tables[key] = torch.from_numpy(idx).to(self.tdev)
-        return self._tables[key]
+        if not cache or idx.size > 65536:
+            return torch.from_numpy(idx).to(self.tdev)
+        return self._cached(self._lru, MAX_TABLES, ("idx", idx.tobytes()), lambda: torch.from_numpy(idx).to(self.tdev))
 
     # ------------------------------------------------------------------ K1: mtmfft
     def mtmfft(self, x, tapers, nfft, scale, polyremoval=-1, demean_taper=False, freq_idx=None,
@@ -116,10 +157,13 @@ class Engine:
         else:
             assert out.is_contiguous()
             so_trial, so_taper, so_freq = Kout * nF * Cn, nF * Cn, Cn
-        _lib.check(self.lib.spyb_mtmfft(
-            x.data_ptr(), B, tstride, N, Cn, tapers.data_ptr(), K, int(nfft), float(scale),
-            int(polyremoval), int(bool(demean_taper)), _ptr(fidx), nF, kind, int(bool(keeptapers)),
-            out.data_ptr(), so_trial, so_taper, so_freq, _ptr(chan_amax), self.stream()))
+        esize = out.element_size()
+        for b0 in range(0, B, MAX_LAUNCH_DIM):            # one launch covers at most 65535 trials (grid.z)
+            nb = min(MAX_LAUNCH_DIM, B - b0)
+            _lib.check(self.lib.spyb_mtmfft(
+                x.data_ptr() + b0 * tstride * 4, nb, tstride, N, Cn, tapers.data_ptr(), K, int(nfft), float(scale),
+                int(polyremoval), int(bool(demean_taper)), _ptr(fidx), nF, kind, int(bool(keeptapers)),
+                out.data_ptr() + b0 * so_trial * esize, so_trial, so_taper, so_freq, _ptr(chan_amax), self.stream()))
         return out
 
     # ------------------------------------------------------------------ K4: mtmconvol
@@ -144,10 +188,19 @@ class Engine:
         so_taper = nF * Cn
         so_frame = Kout * so_taper
         so_trial = n_frames * so_frame
-        _lib.check(self.lib.spyb_mtmconvol(
-            x.data_ptr(), B, tstride, N, Cn, tapers.data_ptr(), K, int(nperseg), int(hop),
-            int(frame_start0), int(n_frames), float(scale), int(polyremoval), _ptr(fidx), nF, kind,
-            int(bool(keeptapers)), out.data_ptr(), so_trial, so_frame, so_taper, so_freq, self.stream()))
+        esize = out.element_size()
+        # one launch covers at most 65535 frames (grid.y) x 65535 trials (grid.z): toi='all' on long trials has more
+        for b0 in range(0, B, MAX_LAUNCH_DIM):
+            nb = min(MAX_LAUNCH_DIM, B - b0)
+            for f0 in range(0, max(n_frames, 1), MAX_LAUNCH_DIM):
+                nf = min(MAX_LAUNCH_DIM, n_frames - f0)
+                if nf <= 0:
+                    break
+                _lib.check(self.lib.spyb_mtmconvol(
+                    x.data_ptr() + b0 * tstride * 4, nb, tstride, N, Cn, tapers.data_ptr(), K, int(nperseg), int(hop),
+                    int(frame_start0 + f0 * hop), int(nf), float(scale), int(polyremoval), _ptr(fidx), nF, kind,
+                    int(bool(keeptapers)), out.data_ptr() + (b0 * so_trial + f0 * so_frame) * esize,
+                    so_trial, so_frame, so_taper, so_freq, self.stream()))
         return out
 
     # ------------------------------------------------------------------ K2 / K3
@@ -269,7 +322,8 @@ class Engine:
         s (float64 / complex128 host arrays), `exponents[s][j]` their powers.  Cached under `key`.
         """
         key = ("conv", key, int(n_samples))
-        if key not in self._tables:
+
+        def make():
             flat = [t for tl in taps_per_scale for t in tl]
             L = hm.conv_same_length(n_samples, flat)
             if L > self.lib.spyb_max_fft_len(1):
@@ -286,12 +340,12 @@ class Engine:
                 for j, (taps, e) in enumerate(zip(tl, el)):
                     kern[si, j] = hm.conv_same_spectrum(taps, n_samples, L)
                     expo[si, j] = e
-            self._tables[key] = dict(L=L, n_scales=nS, max_fac=max_fac,
-                                     kern=torch.from_numpy(kern).to(self.tdev),
-                                     expo=torch.from_numpy(expo).to(self.tdev),
-                                     nfac=torch.from_numpy(nfac).to(self.tdev),
-                                     ones=torch.ones((1, n_samples), dtype=torch.float32, device=self.tdev))
-        return self._tables[key]
+            return dict(L=L, n_scales=nS, max_fac=max_fac,
+                        kern=torch.from_numpy(kern).to(self.tdev),
+                        expo=torch.from_numpy(expo).to(self.tdev),
+                        nfac=torch.from_numpy(nfac).to(self.tdev),
+                        ones=torch.ones((1, n_samples), dtype=torch.float32, device=self.tdev))
+        return self._cached(self._plans, MAX_PLANS, key, make)
 
     def cwt(self, x, plan, output="fourier", out=None):
         """
@@ -323,7 +377,7 @@ class Engine:
         """src [B, R, ...] float32 / complex64 -> [B, len(idx), ...] (rows idx of every trial)."""
         assert src.is_contiguous()
         B, R = src.shape[:2]
-        tidx = self.index_table(idx)
+        tidx = self.index_table(idx, cache=False)
         out = torch.empty((B, tidx.numel()) + tuple(src.shape[2:]), dtype=src.dtype, device=self.tdev)
         words = (2 if src.dtype == torch.complex64 else 1)
         row = int(np.prod(src.shape[2:])) * words
@@ -334,11 +388,12 @@ class Engine:
     # ------------------------------------------------------------------ K7-K9: Granger causality (float64)
     def _workspace(self, nbytes):
         """Grow-only device scratch shared by the Granger kernels."""
-        ws = self._tables.get("workspace")
-        if ws is None or ws.numel() < nbytes:
-            self._tables["workspace"] = None
-            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.tdev)
-            self._tables["workspace"] = ws
+        with self._lock:
+            ws = self._tables.get("workspace")
+            if ws is None or ws.numel() < nbytes:
+                self._tables["workspace"] = None
+                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.tdev)
+                self._tables["workspace"] = ws
         return ws
 
     def regularize_csd(self, csd, cond_max=1e3, eps_max=1e-3, n_steps=15):
@@ -410,6 +465,29 @@ class Engine:
         _lib.check(self.lib.spyb_granger(csd.data_ptr(), H.data_ptr(), Sigma.data_ptr(), nF, Cn, out.data_ptr(),
                                          self.stream()))
         return out
+
+    def sum_trials(self, x, acc=None, alpha=1.0, beta=0.0):
+        """
+        x [B, ...] float32 / complex64 (dense trailing dims) -> acc [...] = beta*acc + alpha * sum_b x[b]: the
+        runtime's `target[()] += res` over a batch (computational_routine.py:1025) and, with alpha = 1/nTrials,
+        its final division (:1030-1032).
+        """
+        assert x.is_cuda and x.dim() >= 2 and x[0].is_contiguous()
+        B = x.shape[0]
+        words = 2 if x.dtype == torch.complex64 else 1
+        n = int(np.prod(x.shape[1:])) * words
+        stride = (x.stride(0) if B > 1 else int(np.prod(x.shape[1:]))) * words
+        if acc is None:
+            acc = torch.empty(x.shape[1:], dtype=x.dtype, device=self.tdev)
+            beta = 0.0
+        assert acc.is_contiguous() and acc.dtype == x.dtype and tuple(acc.shape) == tuple(x.shape[1:])
+        if n % 4 or stride % 4:      # odd sizes: rare (needs a channel count that is not a multiple of 4)
+            red = x.sum(dim=0) * alpha
+            acc.copy_(red if beta == 0.0 else acc * beta + red)
+            return acc
+        _lib.check(self.lib.spyb_sum_trials(x.data_ptr(), B, stride, n, float(alpha), float(beta), acc.data_ptr(),
+                                            self.stream()))
+        return acc
 
     def scale_(self, t, s):
         """In-place t *= s for float32 / complex64 CUDA tensors."""

@@ -175,4 +175,6 @@ def test_sharded_entry_point_with_trivial_exchange(engine):
         return 0
     got = engine.wilson_sf(S, n_iter=40, rtol=1e-9, slab=(0, 33), exchange=exchange)
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and got[2:] == want[2:]
-    assert seen[0] == (0, 21 * 16, 64) and seen[1] == (1, 8, 1) and len(seen) == 2 * got[4]
+    # (1, 8, 1) first and last: the ranks agree on "nobody failed" after the Cholesky and after the loop
+    assert seen[0] == (1, 8, 1) and seen[1] == (0, 21 * 16, 64) and seen[2] == (1, 8, 1)
+    assert seen[-1] == (1, 8, 1) and len(seen) == 2 * got[4] + 2

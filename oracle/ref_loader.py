@@ -89,3 +89,23 @@ def load():
     ns.wavelets_mod = sys.modules["syncopy.specest.wavelets.wavelets"]
     _loaded = ns
     return ns
+
+
+def extract_function(rel_path, name, env):
+    """
+    Compile ONE function of a reference module that cannot be imported as a whole (its module pulls h5py / dask at
+    import time) straight from the file under /root/reference and return it, bound to the globals in `env`.
+    Decorators are dropped (`process_io` only adds the HDF5 plumbing of the parallel runtime).  Nothing is copied
+    into this repository: the source is read and executed where it lies.
+    """
+    import ast
+    path = os.path.join(REF_PKG, rel_path)
+    tree = ast.parse(open(path).read(), filename=path)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = dict(env)
+            exec(compile(mod, path, "exec"), ns)
+            return ns[name]
+    raise KeyError(f"{name} not found in {path}")

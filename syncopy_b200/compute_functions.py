@@ -9,6 +9,8 @@ the arithmetic executed by libspyb200 on the GPU.
     spectral_dyadic_product_cF  <- syncopy/connectivity/ST_compRoutines.py:29-117
     normalize_csd_cF            <- syncopy/connectivity/AV_compRoutines.py:35-112
     granger_cF                  <- syncopy/connectivity/AV_compRoutines.py:292-412
+    cross_covariance_cF         <- syncopy/connectivity/ST_compRoutines.py:465-584
+    ppc_column_cF               <- syncopy/connectivity/ST_compRoutines.py:158-233
     wavelet_cF                  <- syncopy/specest/compRoutines.py:482-595
     superlet_cF                 <- syncopy/specest/compRoutines.py:654-762
 
@@ -236,6 +238,45 @@ def granger_cF(csd_av_dat, rtol=5e-6, nIter=100, cond_max=1e4, chunkShape=None, 
         "initial cond. num--float": np.array(np.float32(ini_cn)),
     }
     return G[None].cpu().numpy(), meta
+
+
+def cross_covariance_cF(trl_dat, samplerate=1, polyremoval=0, timeAxis=0, norm=False, fullOutput=False,
+                        chunkShape=None, noCompute=False):
+    """Single-trial cross-covariance / cross-correlation for all channel pairs (float32, the dry-run dtype)."""
+    dat = _as_time_major(trl_dat, timeAxis)
+    n, n_chan = dat.shape
+    lags = np.arange(0, n // 2) if n % 2 == 0 else np.arange(0, n // 2 + 1)
+    lags = lags * 1 / samplerate
+    out_shape = (len(lags), 1, n_chan, n_chan)
+    if noCompute:
+        return out_shape, np.float32
+    eng = get_engine()
+    x = _trial_to_device(eng, dat)[0]
+    cc = eng.cross_covariance(x, polyremoval=hm.polyremoval_code(polyremoval), norm=norm)
+    res = cc.cpu().numpy()[:, None]
+    return (res, lags) if fullOutput else res
+
+
+def ppc_column_cF(cross_spectrum, trl2_idx=None, hdf5_path=None, chunkShape=None, noCompute=False, cross_spectrum2=None):
+    """
+    One trial pair of the PPC: cos(angle(z1 conj z2)).  The reference reads the second trial from the HDF5 file
+    `hdf5_path` at `trl2_idx`; pass it as `cross_spectrum2` (or give a path -- opened with h5py if that is installed).
+    The whole-dataset path is `syncopy_b200.statistics.ppc`, which needs no pair loop at all.
+    """
+    if noCompute:
+        return cross_spectrum.shape, np.float32
+    if cross_spectrum2 is None:
+        import h5py                                   # only needed for the reference's file-based calling convention
+        with h5py.File(hdf5_path, "r") as h5file:
+            cross_spectrum2 = h5file["data"][trl2_idx]
+    eng = get_engine()
+    z1 = eng.to_device(np.ascontiguousarray(cross_spectrum, dtype=np.complex64), dtype=torch.complex64)
+    z2 = eng.to_device(np.ascontiguousarray(cross_spectrum2, dtype=np.complex64), dtype=torch.complex64)
+    acc = torch.empty_like(z1)
+    eng.unit_accumulate(z1, acc, first=True)
+    eng.unit_accumulate(z2, acc, first=False)
+    # |u1 + u2|^2 = 2 + 2 cos(theta1 - theta2)
+    return eng.ppc_finish(acc, 2).cpu().numpy()
 
 
 def _plan_key(obj):

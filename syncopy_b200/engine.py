@@ -489,6 +489,75 @@ class Engine:
                                             self.stream()))
         return acc
 
+    # ------------------------------------------------------------------ jackknife / PPC / cross-covariance pieces
+    @staticmethod
+    def _words(t):
+        return t.numel() * (2 if t.dtype == torch.complex64 else 1)
+
+    def axpby(self, x, y, a, b, out=None):
+        """out = a*x + b*y element-wise (float32 / complex64 with real factors); y may be None."""
+        assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.complex64)
+        if out is None:
+            out = torch.empty_like(x)
+        assert out.is_contiguous() and out.dtype == x.dtype and out.numel() == x.numel()
+        if y is not None:
+            assert y.is_contiguous() and y.dtype == x.dtype and y.numel() == x.numel()
+        _lib.check(self.lib.spyb_axpby(x.data_ptr(), _ptr(y), float(a), float(b), out.data_ptr(), self._words(x),
+                                       self.stream()))
+        return out
+
+    def sqdev_accumulate(self, avg, x, var):
+        """var += |avg - x|^2 (var float32, avg / x float32 or complex64)."""
+        assert avg.is_contiguous() and x.is_contiguous() and var.is_contiguous() and var.dtype == torch.float32
+        assert avg.dtype == x.dtype and avg.numel() == x.numel() == var.numel()
+        _lib.check(self.lib.spyb_sqdev_accumulate(avg.data_ptr(), x.data_ptr(), var.data_ptr(), x.numel(),
+                                                  int(x.dtype == torch.complex64), self.stream()))
+        return var
+
+    def unit_accumulate(self, z, acc, first):
+        """acc (+)= z / |z| for a complex64 array (single-trial cross spectra)."""
+        assert z.is_contiguous() and acc.is_contiguous() and z.dtype == acc.dtype == torch.complex64
+        _lib.check(self.lib.spyb_unit_accumulate(z.data_ptr(), acc.data_ptr(), z.numel(), int(bool(first)), self.stream()))
+        return acc
+
+    def ppc_finish(self, acc, n_trials):
+        out = torch.empty(acc.shape, dtype=torch.float32, device=self.tdev)
+        _lib.check(self.lib.spyb_ppc_finish(acc.data_ptr(), out.data_ptr(), acc.numel(), int(n_trials), self.stream()))
+        return out
+
+    def cross_covariance(self, x, polyremoval=0, norm=False):
+        """
+        x [N, C] float32 CUDA (one trial) -> [nLags, C, C] float32: single-trial cross-covariance of
+        `cross_covariance_cF` (ST_compRoutines.py:465-584) by FFT: one spectrum per channel, kernel spectra of the
+        time-reversed channels, C^2 inverse transforms in one launch of the wavelet kernel, lag selection.
+        """
+        N, Cn = x.shape
+        n_lags = N // 2 if N % 2 == 0 else N // 2 + 1
+        L = 16
+        while L < 2 * N - 1:
+            L *= 2
+        if L > self.lib.spyb_max_fft_len(1):
+            raise _lib.SpybError(f"cross-covariance of {N} samples needs a circular length of {L} > "
+                                 f"{self.lib.spyb_max_fft_len(1)} (the shared-memory FFT engine's limit)")
+        ones = self._cached(self._lru, MAX_TABLES, ("ones", N), lambda: torch.ones((1, N), dtype=torch.float32, device=self.tdev))
+        xspec = self.mtmfft(x[None], ones, L, 1.0, polyremoval=polyremoval, output="fourier", keeptapers=True)  # [1,1,nF,C]
+        nF = L // 2 + 1
+        xs_t = self.scratch("xcov_xspec_t", (1, Cn, nF), torch.complex64)
+        _lib.check(self.lib.spyb_transpose(xspec.data_ptr(), xs_t.data_ptr(), 1, nF, Cn, 8, self.stream()))
+        kern = self.scratch("xcov_kern", (Cn, 1, L), torch.complex64)
+        n_time = 2 * n_lags + 1
+        shift = N - 1 - n_lags
+        _lib.check(self.lib.spyb_xcov_kernel_spectra(xs_t.data_ptr(), Cn, L, N, shift, kern.data_ptr(), self.stream()))
+        expo = self._cached(self._lru, MAX_TABLES, ("xcov_expo", Cn), lambda: torch.ones((Cn, 1), dtype=torch.float32, device=self.tdev))
+        nfac = self._cached(self._lru, MAX_TABLES, ("xcov_nfac", Cn), lambda: torch.ones(Cn, dtype=torch.int32, device=self.tdev))
+        corr = self.scratch("xcov_corr", (Cn * Cn, n_time), torch.float32)
+        _lib.check(self.lib.spyb_cwt(xs_t.data_ptr(), 1, Cn, L, kern.data_ptr(), expo.data_ptr(), nfac.data_ptr(), Cn, 1,
+                                     n_time, hm.out_kind("real"), 1, corr.data_ptr(), self.stream()))
+        out = torch.empty((n_lags, Cn, Cn), dtype=torch.float32, device=self.tdev)
+        _lib.check(self.lib.spyb_xcov_finish(corr.data_ptr(), xs_t.data_ptr(), Cn, N, n_lags, L, int(bool(norm)),
+                                             out.data_ptr(), self.stream()))
+        return out
+
     def scale_(self, t, s):
         """In-place t *= s for float32 / complex64 CUDA tensors."""
         assert t.is_cuda and t.is_contiguous()

@@ -112,3 +112,149 @@ def test_normalize_csd_live(ref):
         want = ref.csd.normalize_csd(S.copy(), output)
         got = oc.normalize_csd(S.copy(), output)
         assert got.dtype == want.dtype and nerr(got, want) <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------
+# "next" rows: functions whose modules need h5py -- the function bodies are compiled from the reference
+# file itself (ref_loader.extract_function) and run side by side with the restatement
+# ---------------------------------------------------------------------------------------------------------
+def _ref_st_function(ref, name, extra=None):
+    import scipy.signal
+    env = dict(np=np, detrend=scipy.signal.detrend, fftconvolve=scipy.signal.fftconvolve,
+               spectralDTypes=ref.const_def.spectralDTypes, spectralConversions=ref.const_def.spectralConversions)
+    env.update(extra or {})
+    return ref_loader.extract_function("connectivity/ST_compRoutines.py", name, env)
+
+
+@pytest.mark.parametrize("n,pr,norm", [(100, 0, False), (101, 1, True), (64, None, False), (33, 0, True)])
+def test_cross_covariance_live(ref, n, pr, norm):
+    from oracle import statistics as ost
+    fn = _ref_st_function(ref, "cross_covariance_cF")
+    x = np.random.default_rng(n).normal(size=(n, 4)).astype("f4") + np.float32(0.3)
+    want, lags = fn(x.copy(), samplerate=200., polyremoval=pr, norm=norm, fullOutput=True)
+    got, lags2 = ost.cross_covariance_cF(x.copy(), samplerate=200., polyremoval=pr, norm=norm, fullOutput=True)
+    assert got.shape == want.shape and np.array_equal(lags, lags2)
+    assert nerr(got, want) <= 1e-12
+    assert fn(x, noCompute=True)[0] == ost.cross_covariance_cF(x, noCompute=True)[0]
+
+
+def test_ppc_column_live(ref):
+    """ppc_column_cF reads the second trial from HDF5: hand it a stand-in for `h5py.File`."""
+    from oracle import statistics as ost
+    rng = np.random.default_rng(2)
+    a = (rng.normal(size=(1, 6, 3, 3)) + 1j * rng.normal(size=(1, 6, 3, 3))).astype(np.complex64)
+    b = (rng.normal(size=(1, 6, 3, 3)) + 1j * rng.normal(size=(1, 6, 3, 3))).astype(np.complex64)
+
+    class _File:
+        def __init__(self, path, mode):
+            self.path = path
+
+        def __enter__(self):
+            return {"data": {"second": b}}
+
+        def __exit__(self, *exc):
+            return False
+
+    import types
+    fake_h5py = types.SimpleNamespace(File=_File)
+    fn = _ref_st_function(ref, "ppc_column_cF", dict(h5py=fake_h5py))
+    want = fn(a, trl2_idx="second", hdf5_path="unused")
+    assert np.array_equal(want, ost.ppc_column_cF(a, b))
+
+
+class _FakeData:
+    """Just enough of a Syncopy data object (trials stacked along dim 0) for jackknifing.py's function bodies."""
+    _stackingDim = 0
+    _filename = "unused"
+
+    def __init__(self, data=None, samplerate=1.0, dimord=None, n_trials=None):
+        self.samplerate, self.dimord, self.selection, self.cfg = samplerate, dimord, None, {}
+        self._data = None if data is None else np.asarray(data)
+        self._n = n_trials
+
+    # -- the attributes the reference touches
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = np.asarray(value) if not isinstance(value, np.ndarray) else value
+
+    def _reopen(self):
+        pass
+
+    @property
+    def n_trials(self):
+        return self._n if self._n is not None else 1
+
+    @property
+    def sampleinfo(self):
+        step = self._data.shape[0] // self.n_trials
+        return np.array([[k * step, (k + 1) * step] for k in range(self.n_trials)])
+
+    @property
+    def trials(self):
+        step = self._data.shape[0] // self.n_trials
+        return [self._data[k * step:(k + 1) * step] for k in range(self.n_trials)]
+
+    def selectdata(self, inplace=True):
+        self.selection = type("Sel", (), {"trial_ids": list(range(self.n_trials))})()
+
+    def __sub__(self, other):
+        return _FakeData(self._data - other._data, self.samplerate, self.dimord)
+
+    def __rmul__(self, fac):
+        return _FakeData(fac * self._data, self.samplerate, self.dimord)
+
+    trialdefinition = None
+
+
+def _jackknife_functions(ref):
+    from oracle import statistics as ost
+
+    class _H5File:
+        def __init__(self, name, mode="r"):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def create_dataset(self, name, shape, dtype):
+            return np.zeros(shape, dtype=dtype)
+
+    import types
+
+    def spy_mean(obj, dim):
+        assert dim == "trials"
+        return _FakeData(ost.trial_mean(obj.trials), obj.samplerate, obj.dimord)      # summary_stats.py:408-428
+
+    env = dict(np=np, h5py=types.SimpleNamespace(File=_H5File), spy=types.SimpleNamespace(mean=spy_mean),
+               propagate_properties=lambda *a, **k: None, SPYValueError=ValueError, SPYError=RuntimeError)
+    return (ref_loader.extract_function("statistics/jackknifing.py", "trial_avg_replicates", env),
+            ref_loader.extract_function("statistics/jackknifing.py", "bias_var", env))
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.float32])
+def test_jackknife_live(ref, dtype):
+    """trial_avg_replicates / bias_var: the reference's own function bodies on stand-in data objects."""
+    from oracle import statistics as ost
+    ref_replicates, ref_bias_var = _jackknife_functions(ref)
+    rng = np.random.default_rng(4)
+    T = 7
+    x = rng.normal(size=(T, 5, 3, 3))
+    if dtype is np.complex64:
+        x = x + 1j * rng.normal(size=x.shape)
+    x = x.astype(dtype)
+    ens = _FakeData(x.reshape(T * 1, 5, 3, 3), n_trials=T)
+    reps = ref_replicates(ens)
+    mine = ost.trial_avg_replicates(list(x[:, None]))
+    assert np.array_equal(reps.data.reshape(mine.shape), mine)
+    direct = _FakeData(ost.trial_mean(list(x[:, None])), n_trials=1)
+    rep_obj = _FakeData(mine.reshape(T, 5, 3, 3), n_trials=T)
+    bias, var = ref_bias_var(direct, rep_obj)
+    b2, v2 = ost.bias_var(direct.data, list(mine))
+    assert np.array_equal(bias.data, b2) and np.array_equal(var.data, v2)

@@ -236,6 +236,29 @@ int spyb_xcov_finish(const float* corr, const void* xspec, int n_chan, int n_sam
                      float* out, void* stream);
 
 /*
+ * Preprocessing compute functions (syncopy/preproc/compRoutines.py).
+ *   spyb_sosfilt      IIR filtering with second-order sections, replaces scipy.signal.sosfilt (twopass = 0: zero initial
+ *                     state) and scipy.signal.sosfiltfilt (twopass = 1: odd extension by `edge` samples, steady-state
+ *                     initial conditions `zi_host` [n_sections][2] scaled by the edge sample, forward + backward pass) as
+ *                     called by but_filtering_cF (:175-276).  sos_host [n_sections][6] float64 (host), recursion in
+ *                     float64, out float32 [trial][sample][channel]; scratch float64 [trial][n_samples + 2 edge][channel].
+ *   spyb_upfirdn      polyphase FIR resampling, replaces scipy.signal.upfirdn inside resample_poly as called by
+ *                     resample_cF (:541-616, preproc/resampling.py:14-79): out[m] = sum_i x[i] h[(m + first_row) down -
+ *                     i up], h float64 [len_h] (device; already zero-padded and scaled by `up` like resample_poly does),
+ *                     accumulation in float64.
+ *   spyb_standardize  (x - mean) / std per channel (standardize_cF, :765-832; detrending first via spyb_detrend).
+ *   spyb_rectify      |x| (rectify_cF, :303-338).
+ * The windowed-sinc FIR filters of sinc_filtering_cF (:27-148, preproc/firws.py) and the analytic signal of hilbert_cF
+ * (:365-419) are 'same' / circular convolutions and run on spyb_cwt with host-designed kernels.
+ */
+int spyb_sosfilt(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, const double* sos_host,
+                 int n_sections, const double* zi_host, int edge, int twopass, double* scratch, float* out, void* stream);
+int spyb_upfirdn(const float* x, int n_trials, long long trial_stride, int n_in, int n_chan, const double* h, int len_h,
+                 int up, int down, int first_row, int n_out, float* out, void* stream);
+int spyb_standardize(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, float* out, void* stream);
+int spyb_rectify(const float* x, float* out, long long n, void* stream);
+
+/*
  * Granger causality path (float64 / complex128 like the reference, AV_compRoutines.py:395).  These three calls
  * synchronise `stream` internally: the regularisation ladder and Wilson's iteration are data dependent.
  * `work` is caller-owned device scratch of at least spyb_*_workspace_bytes().  `_host` pointers are host memory.

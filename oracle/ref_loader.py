@@ -40,6 +40,8 @@ _LOAD_ORDER = [
     ("syncopy.connectivity.csd", "connectivity/csd.py"),
     ("syncopy.connectivity.wilson_sf", "connectivity/wilson_sf.py"),
     ("syncopy.connectivity.granger", "connectivity/granger.py"),
+    ("syncopy.preproc.firws", "preproc/firws.py"),
+    ("syncopy.preproc.resampling", "preproc/resampling.py"),
 ]
 
 _loaded = None
@@ -71,7 +73,7 @@ def load():
     top.__tbcount__ = 5       # shared/errors.py reads this
     top.__logdir__ = None
     top.__version__ = "2023.09-bypath"
-    for pkg in ("specest", "connectivity", "shared"):
+    for pkg in ("specest", "connectivity", "shared", "preproc"):
         _stub(f"syncopy.{pkg}", os.path.join(REF_PKG, pkg))
     _stub("syncopy.specest.wavelets", os.path.join(REF_PKG, "specest", "wavelets"))
 
@@ -80,6 +82,9 @@ def load():
         spec = importlib.util.spec_from_file_location(dotted, os.path.join(REF_PKG, rel))
         mod = importlib.util.module_from_spec(spec)
         sys.modules[dotted] = mod
+        if dotted == "syncopy.preproc.resampling":
+            # `from syncopy.preproc import firws` inside resampling.py
+            sys.modules["syncopy.preproc"].firws = sys.modules["syncopy.preproc.firws"]
         if dotted == "syncopy.specest.wavelet":
             # `from syncopy.specest.wavelets import cwt` inside wavelet.py
             sys.modules["syncopy.specest.wavelets"].cwt = sys.modules[

@@ -58,6 +58,10 @@ PROTOTYPES = {
     "spyb_ppc_finish": (_i, [_vp, _vp, _ll, _i, _vp]),
     "spyb_xcov_kernel_spectra": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "spyb_xcov_finish": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "spyb_sosfilt": (_i, [_vp, _i, _ll, _i, _i, _dp, _i, _dp, _i, _i, _vp, _vp, _vp]),
+    "spyb_upfirdn": (_i, [_vp, _i, _ll, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "spyb_standardize": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp]),
+    "spyb_rectify": (_i, [_vp, _vp, _ll, _vp]),
     "spyb_regularize_workspace_bytes": (_ll, [_i, _i]),
     "spyb_regularize_csd": (_i, [_vp, _i, _i, _d, _d, _i, _vp, _dp, _dp, _vp, _ll, _vp]),
     "spyb_wilson_workspace_bytes": (_ll, [_i, _i]),

@@ -237,6 +237,27 @@ int spyb_xcov_finish(const float* corr, const void* xspec, int n_chan, int n_sam
     return xcov_finish(corr, xspec, n_chan, n_samples, n_lags, n_dft, norm, out, static_cast<cudaStream_t>(stream));
 }
 
+int spyb_sosfilt(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, const double* sos_host,
+                 int n_sections, const double* zi_host, int edge, int twopass, double* scratch, float* out, void* stream) {
+    if (!sos_host) return fail("sos_host must not be NULL");
+    return sosfilt(x, n_trials, trial_stride, n_samples, n_chan, sos_host, n_sections, zi_host, edge, twopass, scratch, out,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int spyb_upfirdn(const float* x, int n_trials, long long trial_stride, int n_in, int n_chan, const double* h, int len_h,
+                 int up, int down, int first_row, int n_out, float* out, void* stream) {
+    return upfirdn(x, n_trials, trial_stride, n_in, n_chan, h, len_h, up, down, first_row, n_out, out,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int spyb_standardize(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, float* out, void* stream) {
+    return standardize(x, n_trials, trial_stride, n_samples, n_chan, out, static_cast<cudaStream_t>(stream));
+}
+
+int spyb_rectify(const float* x, float* out, long long n, void* stream) {
+    return rectify(x, out, n, static_cast<cudaStream_t>(stream));
+}
+
 long long spyb_regularize_workspace_bytes(int n_freq, int n_chan) {
     return regularize_workspace_bytes(n_freq, n_chan);
 }

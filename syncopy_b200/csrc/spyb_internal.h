@@ -93,6 +93,14 @@ int xcov_kernel_spectra(const void* xspec, int n_chan, int L, int n, int shift, 
 int xcov_finish(const float* corr, const void* xspec, int n_chan, int n, int n_lags, int L, int norm, float* out,
                 cudaStream_t st);
 
+// Preprocessing (preproc.cu)
+int sosfilt(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, const double* sos_host,
+            int n_sections, const double* zi_host, int edge, int twopass, double* scratch, float* out, cudaStream_t st);
+int upfirdn(const float* x, int n_trials, long long trial_stride, int n_in, int n_chan, const double* h, int len_h,
+            int up, int down, int m0, int n_out, float* out, cudaStream_t st);
+int standardize(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, float* out, cudaStream_t st);
+int rectify(const float* x, float* out, long long n, cudaStream_t st);
+
 // Granger path: regularisation, Wilson spectral factorisation, Geweke-Granger formula (wilson.cu); FP64
 long long regularize_workspace_bytes(int n_freq, int n_chan);
 int regularize_csd(const void* csd_c64, int n_freq, int n_chan, double cond_max, double eps_max, int n_steps,

@@ -558,6 +558,56 @@ class Engine:
                                              out.data_ptr(), self.stream()))
         return out
 
+    # ------------------------------------------------------------------ preprocessing
+    def fir_same(self, x, taps, key, output="real"):
+        """
+        x [B, N, C] float32 -> [B, N, C]: scipy.signal.convolve(x, taps[:, None], 'same') per channel as an FFT
+        convolution on the wavelet kernel (one 'scale'); complex taps + `output` give analytic-signal conversions.
+        """
+        B, N, Cn = x.shape
+        plan = self.conv_plan(("fir", key), N, [[np.asarray(taps)]], [[1.0]])
+        return self.cwt(x, plan, output=output)[:, :, 0, :]
+
+    def sosfilt(self, x, sos, twopass):
+        """x [B, N, C] float32 -> float32: scipy.signal.sosfilt (twopass=False) / sosfiltfilt (True), float64 recursion."""
+        import ctypes as C
+        tstride = _trial_layout(x)
+        B, N, Cn = x.shape
+        sos = np.ascontiguousarray(sos, dtype=np.float64)
+        S = sos.shape[0]
+        out = torch.empty((B, N, Cn), dtype=torch.float32, device=self.tdev)
+        edge, zi, scratch = 0, None, None
+        if twopass:
+            edge, zi = hm.sosfiltfilt_plan(sos)
+            scratch = self.scratch("sos_fwd", (B, N + 2 * edge, Cn), torch.float64)
+        zi_p = zi.ctypes.data_as(C.POINTER(C.c_double)) if zi is not None else None
+        _lib.check(self.lib.spyb_sosfilt(x.data_ptr(), B, tstride, N, Cn, sos.ctypes.data_as(C.POINTER(C.c_double)), S,
+                                         zi_p, int(edge), int(bool(twopass)), _ptr(scratch), out.data_ptr(), self.stream()))
+        return out
+
+    def resample_poly(self, x, h, up, down, first_row, n_out):
+        """x [B, N, C] float32 -> [B, n_out, C]: rows first_row .. first_row + n_out of upfirdn(h, x, up, down)."""
+        tstride = _trial_layout(x)
+        B, N, Cn = x.shape
+        hd = torch.from_numpy(np.ascontiguousarray(h, dtype=np.float64)).to(self.tdev)
+        out = torch.empty((B, n_out, Cn), dtype=torch.float32, device=self.tdev)
+        _lib.check(self.lib.spyb_upfirdn(x.data_ptr(), B, tstride, N, Cn, hd.data_ptr(), hd.numel(), int(up), int(down),
+                                         int(first_row), int(n_out), out.data_ptr(), self.stream()))
+        return out
+
+    def standardize(self, x):
+        tstride = _trial_layout(x)
+        B, N, Cn = x.shape
+        out = torch.empty((B, N, Cn), dtype=torch.float32, device=self.tdev)
+        _lib.check(self.lib.spyb_standardize(x.data_ptr(), B, tstride, N, Cn, out.data_ptr(), self.stream()))
+        return out
+
+    def rectify(self, x):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        out = torch.empty_like(x)
+        _lib.check(self.lib.spyb_rectify(x.data_ptr(), out.data_ptr(), x.numel(), self.stream()))
+        return out
+
     def scale_(self, t, s):
         """In-place t *= s for float32 / complex64 CUDA tensors."""
         assert t.is_cuda and t.is_contiguous()

@@ -231,3 +231,140 @@ def conv_same_spectrum(taps, n_samples, L):
     h = np.zeros(L, dtype=np.complex128)
     h[d % L] = taps[d + c0]
     return np.fft.fft(h) / L
+
+
+# ---------------------------------------------------------------------------------------------------------
+# preprocessing: host-side filter design (float64 tables, like the taper tables) for the kernels of csrc/preproc.cu
+# ---------------------------------------------------------------------------------------------------------
+
+def windowed_sinc(window, order, f_c):
+    """syncopy/preproc/firws.py:109-148: windowed sinc low-pass of `order + 1` taps, unity gain."""
+    import scipy.signal.windows as sci_win
+    omega_c = 2 * np.pi * f_c
+    win = getattr(sci_win, window)(order + 1)
+    m_half = np.arange(1, order / 2 + 1)
+    kernel = np.sin(omega_c * m_half) / m_half
+    kernel = np.hstack([kernel[::-1], omega_c, kernel]) * win
+    return kernel / kernel.sum()
+
+
+def _invert_sinc(kernel):
+    """firws.py:151-169: spectral inversion (low-pass -> high-pass); the kernel length is odd."""
+    kernel = -kernel
+    kernel[len(kernel) // 2] += 1
+    return kernel
+
+
+def design_wsinc(window, order, f_c, filter_type="lp"):
+    """firws.py:49-106: low-, high-, band-pass and band-stop windowed-sinc kernels (f_c in units of the sampling rate)."""
+    if order % 2 != 0:
+        order += 1
+    if filter_type == "lp":
+        return windowed_sinc(window, order, f_c)
+    if filter_type == "hp":
+        return _invert_sinc(windowed_sinc(window, order, f_c))
+    if filter_type == "bp":
+        f_hp, f_lp = f_c
+    elif filter_type == "bs":
+        f_lp, f_hp = f_c
+    else:
+        raise ValueError(f"unknown filter type {filter_type!r}")
+    kernel = windowed_sinc(window, order, f_lp) + _invert_sinc(windowed_sinc(window, order, f_hp))
+    if filter_type == "bp":
+        kernel[len(kernel) // 2] -= 1
+    return kernel
+
+
+def minphaserceps(fkernel):
+    """firws.py:172-222: minimum-phase version of a FIR kernel through the real cepstrum (host, float64)."""
+    n = len(fkernel)
+    n_fft = int(2 ** np.ceil(np.log2(n * 1e3)))
+    spec = np.abs(np.fft.fft(fkernel, n_fft))
+    spec[spec < 1e-8] = 1e-8
+    ceps = np.real(np.fft.ifft(np.log(spec)))
+    ires = np.hstack([ceps[1:n_fft // 2], 0]) + np.conj(ceps[n_fft // 2:n_fft + 1][::-1])
+    ceps = np.hstack([ceps[0], ires, np.zeros(n_fft // 2 - 2)])
+    return np.real(np.fft.ifft(np.exp(np.fft.fft(ceps))))[:n]
+
+
+def butter_sos(order, freq, filter_type, samplerate):
+    """The design call of but_filtering_cF (compRoutines.py:263): second-order sections, float64 [S, 6]."""
+    import scipy.signal as sci
+    return np.ascontiguousarray(sci.butter(order, freq, filter_type, fs=samplerate, output="sos"), dtype=np.float64)
+
+
+def sosfiltfilt_plan(sos):
+    """Edge length and steady-state initial conditions exactly as scipy.signal.sosfiltfilt derives them
+    (padtype='odd', padlen=None): ntaps = 2 S + 1 - min(#zero b2, #zero a2), padlen = 3 ntaps, zi = sosfilt_zi."""
+    import scipy.signal as sci
+    n_sections = sos.shape[0]
+    ntaps = 2 * n_sections + 1
+    ntaps -= min((sos[:, 2] == 0).sum(), (sos[:, 5] == 0).sum())
+    return int(3 * ntaps), np.ascontiguousarray(sci.sosfilt_zi(sos), dtype=np.float64)
+
+
+def analytic_kernel(n):
+    """
+    scipy.signal.hilbert multiplies the length-n spectrum by h (1 at DC / Nyquist, 2 at positive, 0 at negative
+    frequencies): the analytic signal is the CIRCULAR convolution of x with a = ifft(h).  Returned: the 2n - 1 taps
+    a[d mod n], d = -(n-1) .. n-1, so that a plain 'same' convolution (centre n - 1) reproduces the circular one.
+    """
+    h = np.zeros(n)
+    if n % 2 == 0:
+        h[0] = h[n // 2] = 1
+        h[1:n // 2] = 2
+    else:
+        h[0] = 1
+        h[1:(n + 1) // 2] = 2
+    a = np.fft.ifft(h)
+    d = np.arange(-(n - 1), n)
+    return a[d % n]
+
+
+def resample_plan(n_in, orig_fs, new_fs, lpfreq=None, order=None):
+    """
+    Filter and bookkeeping of `resample` (syncopy/preproc/resampling.py:14-79) + scipy.signal.resample_poly:
+    returns (h float64 -- zero-padded and scaled by `up` as resample_poly does --, up, down, first kept row, n_out).
+    """
+    import fractions
+    import math
+    frac = fractions.Fraction.from_float(new_fs / orig_fs).limit_denominator()
+    up, down = frac.numerator, frac.denominator
+    fs_ratio = new_fs / orig_fs
+    if lpfreq is None:
+        f_c = 0.5 * fs_ratio
+    elif lpfreq == -1:
+        f_c = None
+    else:
+        f_c = lpfreq / orig_fs
+    if order is None:
+        order = n_in * up
+        order = 10000 if order > 10000 else order
+    if f_c:
+        window = design_wsinc("hamming", order=order, f_c=f_c / up)
+    else:
+        window = None
+    g = math.gcd(up, down)
+    up //= g
+    down //= g
+    n_out = n_in * up
+    n_out = n_out // down + bool(n_out % down)
+    if window is not None:
+        half_len = (window.size - 1) // 2
+        h = np.array(window, dtype=np.float64)
+    else:
+        from scipy.signal import firwin
+        max_rate = max(up, down)
+        half_len = 10 * max_rate
+        h = firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)).astype(np.float32).astype(np.float64)
+    h = h * up
+    n_pre_pad = down - half_len % down
+    n_post_pad = 0
+    n_pre_remove = (half_len + n_pre_pad) // down
+
+    def output_len(len_h):
+        return (((n_in - 1) * up + len_h) - 1) // down + 1
+    while output_len(h.size + n_pre_pad + n_post_pad) < n_out + n_pre_remove:
+        n_post_pad += 1
+    h = np.concatenate([np.zeros(n_pre_pad), h, np.zeros(n_post_pad)])
+    return np.ascontiguousarray(h), int(up), int(down), int(n_pre_remove), int(n_out)

@@ -258,3 +258,62 @@ def test_jackknife_live(ref, dtype):
     bias, var = ref_bias_var(direct, rep_obj)
     b2, v2 = ost.bias_var(direct.data, list(mine))
     assert np.array_equal(bias.data, b2) and np.array_equal(var.data, v2)
+
+
+# ---- preprocessing: firws.py / resampling.py load by path, the cF bodies are compiled in place ----------
+def _ref_preproc_cf(ref, name):
+    import logging
+    import platform
+    import scipy.signal
+    env = dict(np=np, sci=scipy.signal, logging=logging, platform=platform,
+               design_wsinc=ref.firws.design_wsinc, apply_fir=ref.firws.apply_fir, minphaserceps=ref.firws.minphaserceps,
+               downsample=ref.resampling.downsample, resample=ref.resampling.resample,
+               spectralDTypes=ref.const_def.spectralDTypes, spectralConversions=ref.const_def.spectralConversions)
+    return ref_loader.extract_function("preproc/compRoutines.py", name, env)
+
+
+def _noise(n, c, seed):
+    return np.random.default_rng(seed).normal(size=(n, c)).astype("f4") + np.float32(0.2)
+
+
+@pytest.mark.parametrize("ft,freq,order,direction,pr", [
+    ("lp", 30., None, "onepass", None), ("hp", 10., 100, "twopass", 0), ("bp", np.array([10., 40.]), 201, "onepass", 1),
+    ("bs", np.array([45., 55.]), 300, "onepass-minphase", None)])
+def test_sinc_filtering_live(ref, ft, freq, order, direction, pr):
+    from oracle import preproc as opp
+    fn = _ref_preproc_cf(ref, "sinc_filtering_cF")
+    x = _noise(500, 3, 1)
+    kw = dict(samplerate=200., filter_type=ft, freq=freq, order=order, direction=direction, polyremoval=pr)
+    want, meta = fn(x.copy(), **kw)
+    got, meta2 = opp.sinc_filtering_cF(x.copy(), **kw)
+    assert nerr(got, want) <= 1e-12 and bool(meta["has_nan"]) == bool(meta2["has_nan"])
+
+
+@pytest.mark.parametrize("ft,freq,order,direction", [("lp", 30., 6, "twopass"), ("hp", 5., 4, "onepass"),
+                                                      ("bp", [10., 40.], 3, "twopass"), ("bs", [45., 55.], 2, "onepass")])
+def test_but_filtering_live(ref, ft, freq, order, direction):
+    from oracle import preproc as opp
+    fn = _ref_preproc_cf(ref, "but_filtering_cF")
+    x = _noise(400, 4, 2)
+    kw = dict(samplerate=200., filter_type=ft, freq=freq, order=order, direction=direction, polyremoval=0)
+    want, _ = fn(x.copy(), **kw)
+    got, _ = opp.but_filtering_cF(x.copy(), **kw)
+    assert nerr(got, want) <= 1e-12
+
+
+def test_hilbert_resample_misc_live(ref):
+    from oracle import preproc as opp
+    x = _noise(333, 3, 3)
+    for output in ("abs", "complex", "angle", "real", "imag"):
+        assert nerr(opp.hilbert_cF(x.copy(), output=output), _ref_preproc_cf(ref, "hilbert_cF")(x.copy(), output=output)) <= 1e-12
+    for kw in (dict(samplerate=1000., new_samplerate=250.), dict(samplerate=500., new_samplerate=333., order=100),
+               dict(samplerate=200., new_samplerate=300., lpfreq=60.)):
+        want = _ref_preproc_cf(ref, "resample_cF")(x.copy(), **kw)
+        got = opp.resample_cF(x.copy(), **kw)
+        assert got.shape == want.shape and nerr(got, want) <= 1e-12
+        assert opp.resample_cF(x, noCompute=True, **kw) == _ref_preproc_cf(ref, "resample_cF")(x, noCompute=True, **kw)
+    assert np.array_equal(opp.rectify_cF(x), _ref_preproc_cf(ref, "rectify_cF")(x))
+    assert nerr(opp.standardize_cF(x.copy(), polyremoval=1), _ref_preproc_cf(ref, "standardize_cF")(x.copy(), polyremoval=1)) <= 1e-12
+    a, _ = opp.detrending_cF(x.copy(), polyremoval=1)
+    b, _ = _ref_preproc_cf(ref, "detrending_cF")(x.copy(), polyremoval=1)
+    assert nerr(a, b) <= 1e-12

@@ -431,26 +431,34 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                         // fp32 planes are in the TMA layout: offset = c_blk*2048 + row*128 + c_in*4 with the 32-byte
                         // chunk index XOR-ed with row % 4; the bf16 copies go to the SWIZZLE_128B MN-major layout:
                         // blk64*2048 + (row/8)*1024 + (row%8)*128 + ((c%64/8) ^ (row%8))*16 + (c%8)*2
+                        // Thread -> chunk mapping: lane bits = (16-byte chunk 0..7 | low bit of the 32-channel block |
+                        // row bit 0), so a warp's bf16 stores cover two full 128-byte rows (conflict free; with 32
+                        // consecutive chunks of one block they fell into half the banks, 4-way conflicts) and every
+                        // address below is a per-thread constant plus a compile-time constant of the unrolled loop.
                         uint8_t* h16 = reinterpret_cast<uint8_t*>(hi) + 2 * TC_PLANE;
-#pragma unroll 4
-                        for (int q = ct; q < (2 * TC_PLANE) / 16; q += TC_CONV_THREADS) {
-                            const float4 x = hi[q];
+                        const uint32_t chunk = (uint32_t)ct & 7u, blk_lo = ((uint32_t)ct >> 3) & 1u, row_lo = ((uint32_t)ct >> 4) & 7u;
+                        const uint32_t src0 = blk_lo * 2048u + row_lo * 128u + chunk * 16u;       // + (it&1)*1024 + (it&2)*2048 + (it&4)*2048
+                        // un-swizzle (row % 4 is row_lo % 4 for both values of row bit 3)
+                        const uint32_t lin = (chunk * 16u) ^ ((row_lo & 3u) << 5);
+                        const uint32_t c_in = (lin >> 2) & 31u;
+                        const uint32_t c64 = blk_lo * 32u + c_in;                                  // channel within the 64-block
+                        const uint32_t dst0 = (row_lo << 7) | ((((c64 >> 3) & 7u) ^ row_lo) << 4) | ((c64 & 7u) << 1);
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const uint32_t r8 = (uint32_t)it & 1u, bh = ((uint32_t)it >> 1) & 1u, pl = (uint32_t)it >> 2;
+                            float4* src = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(hi) + pl * TC_PLANE + bh * 4096u + r8 * 1024u + src0);
+                            const float4 x = *src;
                             float4 h;
                             if (a.rewrite_hi) {
                                 h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
-                                hi[q] = h;
+                                *src = h;
                             } else {                             // the tensor core ignores the low 13 mantissa bits
                                 h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
                                 h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
                                 h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
                                 h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
                             }
-                            const uint32_t pl = (uint32_t)q / (TC_PLANE / 16);               // 0 re, 1 im
-                            const uint32_t phi = ((uint32_t)q % (TC_PLANE / 16)) * 16u;
-                            const uint32_t lin = phi ^ (((phi >> 7) & 3u) << 5);
-                            const uint32_t c = ((lin >> 11) << 5) | ((lin >> 2) & 31u), row = (lin >> 7) & 15u;
-                            const uint32_t off = ((c >> 6) << 11) | ((row >> 3) << 10) | ((row & 7u) << 7) |
-                                                 ((((c >> 3) & 7u) ^ (row & 7u)) << 4) | ((c & 7u) << 1);
+                            const uint32_t off = bh * 2048u + r8 * 1024u + dst0;
                             __nv_bfloat162 a0 = __floats2bfloat162_rn(h.x, h.y), a1 = __floats2bfloat162_rn(h.z, h.w);
                             __nv_bfloat162 l0 = __floats2bfloat162_rn(x.x - h.x, x.y - h.y);
                             __nv_bfloat162 l1 = __floats2bfloat162_rn(x.z - h.z, x.w - h.w);

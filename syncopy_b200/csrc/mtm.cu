@@ -356,6 +356,8 @@ int mtm_frames(const MtmFramesDesc& d, cudaStream_t stream) {
     if (!pl->bluestein && !force_stockham) {
         const int rt = mtm_launch_tma(pl->log2n, a, stream);
         if (rt >= 0) return rt;
+        const int r8 = mtm_launch_r8(pl->log2n, a, stream);
+        if (r8 >= 0) return r8;
         const int rc = mtm_launch_dif(pl->log2n, a, stream);
         if (rc >= 0) return rc;
     }

@@ -36,5 +36,7 @@ struct MtmArgs {
 int mtm_launch_dif(int log2n, const MtmArgs& a, cudaStream_t stream);
 // mtm_tma.cu: persistent TMA-pipelined kernel for N = 4096 and full 8-channel tiles; -1 when not eligible
 int mtm_launch_tma(int log2n, const MtmArgs& a, cudaStream_t stream);
+// mtm_r8.cu: 512-point windows (radix-8 passes, frame resident in registers across tapers); -1 when not eligible
+int mtm_launch_r8(int log2n, const MtmArgs& a, cudaStream_t stream);
 
 }  // namespace spyb

@@ -41,79 +41,11 @@
 
 #include "common.cuh"
 #include "mtm_args.cuh"
+#include "packed.cuh"
 #include "spyb_internal.h"
 
 namespace spyb {
 namespace {
-
-// ---- packed complex arithmetic: one 64-bit register pair = (re, im) ------------------------------------------
-typedef unsigned long long c2;
-
-__device__ __forceinline__ c2 pk(float a, float b) {
-    c2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ float re(c2 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    (void)b;
-    return a;
-}
-__device__ __forceinline__ float im(c2 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    (void)a;
-    return b;
-}
-__device__ __forceinline__ c2 add2(c2 a, c2 b) { c2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ c2 sub2(c2 a, c2 b) { c2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ c2 mul2(c2 a, c2 b) { c2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ c2 fma2(c2 a, c2 b, c2 c) {
-    c2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ c2 bc(float s) { return pk(s, s); }
-__device__ __forceinline__ c2 mul_mi(c2 x) { return pk(im(x), -re(x)); }                       // x * (-i)
-__device__ __forceinline__ c2 cmul2(c2 x, float wx, float wy) {                                // x * (wx + i wy)
-    return fma2(pk(-im(x), re(x)), bc(wy), mul2(x, bc(wx)));
-}
-
-__device__ __forceinline__ void dft4(c2& a0, c2& a1, c2& a2, c2& a3) {
-    const c2 s02 = add2(a0, a2), d02 = sub2(a0, a2), s13 = add2(a1, a3), d13 = sub2(a1, a3);
-    a0 = add2(s02, s13);
-    a2 = sub2(s02, s13);
-    const c2 t = mul_mi(d13);          // X1 = d02 - i d13, X3 = d02 + i d13
-    a1 = add2(d02, t);
-    a3 = sub2(d02, t);
-}
-
-// forward 16-point DFT; X[k] ends up in x[reg16(k)] (same conventions as Radix<16> in fft_core.cuh)
-__host__ __device__ constexpr int reg16(int k) { return (k >> 2) + 4 * (k & 3); }
-__device__ __forceinline__ void dft16(c2 (&x)[16]) {
-    dft4(x[0], x[4], x[8], x[12]);
-    dft4(x[1], x[5], x[9], x[13]);
-    dft4(x[2], x[6], x[10], x[14]);
-    dft4(x[3], x[7], x[11], x[15]);
-    const float h = 0.70710678118654752440f;    // cos(pi/4)
-    const float c1 = 0.92387953251128675613f;   // cos(pi/8)
-    const float s1 = 0.38268343236508977173f;   // sin(pi/8)
-    // x[i + 4q] *= W16^{i q}
-    x[5] = cmul2(x[5], c1, -s1);                                           // W^1
-    x[9] = mul2(add2(x[9], mul_mi(x[9])), bc(h));                          // W^2 = (1 - i)/sqrt2
-    x[13] = cmul2(x[13], s1, -c1);                                         // W^3
-    x[6] = mul2(add2(x[6], mul_mi(x[6])), bc(h));                          // W^2
-    x[10] = mul_mi(x[10]);                                                 // W^4 = -i
-    x[14] = mul2(sub2(mul_mi(x[14]), x[14]), bc(h));                       // W^6 = (-1 - i)/sqrt2
-    x[7] = cmul2(x[7], s1, -c1);                                           // W^3
-    x[11] = mul2(sub2(mul_mi(x[11]), x[11]), bc(h));                       // W^6
-    x[15] = cmul2(x[15], -c1, s1);                                         // W^9
-    dft4(x[0], x[1], x[2], x[3]);
-    dft4(x[4], x[5], x[6], x[7]);
-    dft4(x[8], x[9], x[10], x[11]);
-    dft4(x[12], x[13], x[14], x[15]);
-}
 
 // ---- mbarrier / TMA wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -154,7 +86,6 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2_) : "memory");
 }
 
-__device__ __forceinline__ c2 cmulc2(c2 x, c2 w) { return cmul2(x, re(w), im(w)); }
 
 // ---- geometry ------------------------------------------------------------------------------------------------------
 constexpr int LOG2N = 12;

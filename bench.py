@@ -71,8 +71,7 @@ def config_dict(args, n_gpus):
         "trials_per_gpu": N_TRIALS, "n_channels": N_CHAN, "n_samples": N_SAMPLES, "n_tapers": w["K"],
         "parallelism": f"trial-sharded x{n_gpus}" + (
             "; upper CSD tiles stored straight into the frequency-slab owner's slot buffer over NVLink P2P from the "
-            "tcgen05 epilogue, counter all-reduce as barrier, per-slab normalisation on a second stream overlapping the "
-            "next step's FFT / contraction, result left sharded by frequency slab"
+            "tcgen05 epilogue, counter all-reduce as barrier, result left sharded by frequency slab"
             if n_gpus > 1 and getattr(args, "csd_impl", 0) in (0, 2) else
             (" + NCCL all-reduce of the CSD sum" if n_gpus > 1 else "")),
         "l2_policy": "inputs (839 MB/step) and spectra exceed the 126 MB L2; no explicit flush",
@@ -471,9 +470,9 @@ class Cfg2Step:
         if self.mode == "tiles":
             self.ex.barrier(self.n_local, n_total=self.total_trials)   # counter all-reduce: every rank's tiles landed
             rec(3)
-            # N > 1: the normalisation of this step runs on a second stream and overlaps the next step's K1 / K2
-            # (which write the other slot buffer); the next barrier waits for it
-            self.ex.normalize(self.total_trials, output="abs", out=self.coh[0], overlap=self.world > 1)
+            # (running this on a second stream under the next step's K1 was measured slower at N = 2: the persistent
+            # FFT blocks and the normalisation compete for SMs and HBM, 1.72 -> 1.84 ms per step)
+            self.ex.normalize(self.total_trials, output="abs", out=self.coh[0])
             rec(4)
             return
         if self.world > 1:
@@ -775,19 +774,6 @@ def run_gpu_arm(args):
     assert dmax < 1e-5, f"e2e result deviates from device-resident result ({dmax})"
 
     launches_per_step = _count_launches_per_step(stepper)      # every rank: the step contains a collective for N > 1
-    k3_alone_ms = None
-    if world > 1 and stepper.mode == "tiles":
-        # the overlapped normalisation does not show up between the step's event marks: time the kernel on its own
-        torch.cuda.synchronize(dev)
-        ex = stepper.ex
-        k0, k1 = ev(), ev()
-        k0.record()
-        for _ in range(3):
-            eng.csd_normalize_tiles(ex.slots[0][:, :ex.nf_local], N_CHAN, output="abs", pre_scale=1.0 / total_trials,
-                                    out=stepper.coh[0])
-        k1.record()
-        torch.cuda.synchronize(dev)
-        k3_alone_ms = k0.elapsed_time(k1) / 3
     peaks = load_peaks()
     configs = None
     if not args.no_configs:
@@ -843,9 +829,6 @@ def run_gpu_arm(args):
             "normalize (K3)": {"ms": float(norm_ms), "bound": "hbm",
                                "achieved_gbs": k3_bytes / max(norm_ms, 1e-9) / 1e6},
         }
-        if k3_alone_ms is not None:
-            kernels["normalize (K3)"] = {"ms": float(k3_alone_ms), "bound": "hbm", "achieved_gbs": k3_bytes / k3_alone_ms / 1e6,
-                                         "overlapped": "runs on a second stream under the next step's K1 / K2; timed alone here"}
         if fused:       # K2's epilogue normalises: one kernel, coherence written once (4 B per element)
             del kernels["barrier"], kernels["normalize (K3)"]
             kernels["csd (K2)"]["bytes_gbs"] = (spec_bytes + csd_bytes / 2) / (csd_ms * 1e-3) / 1e9

@@ -55,6 +55,16 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
     return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 
+// upper-triangular 128 x 128 tiles of an nb x nb block matrix, row-major: t = 0 -> (0,0), 1 -> (0,1), ..., nb -> (1,1), ...
+__host__ __device__ __forceinline__ int tri_tiles(int nb) { return nb * (nb + 1) / 2; }
+__host__ __device__ __forceinline__ int tri_diag(int nb, int b) { return b * nb - b * (b - 1) / 2; }   // tile (b, b)
+__host__ __device__ __forceinline__ void tri_decode(int nb, int t, int& ti, int& tj) {
+    ti = 0;
+    int row = nb;
+    while (t >= row) { t -= row; ++ti; --row; }
+    tj = ti + t;
+}
+
 // output conversions of syncopy/shared/const_def.py:25-40 (spectralConversions)
 enum OutKind : int {
     OUT_POW = 0, OUT_ABS = 1, OUT_FOURIER = 2, OUT_REAL = 3, OUT_IMAG = 4,

@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(256) csd_normalize_tiles_kernel(const float2* 
     __shared__ float2 s_t[32][33];
     __shared__ int s_general;
     const int t = blockIdx.y, f = blockIdx.z;
-    const int ti = n_tiles == 1 ? 0 : (t >> 1), tj = n_tiles == 1 ? 0 : ((t + 1) >> 1);
+    const int nb = C / 128;
+    int ti, tj;
+    tri_decode(nb, t, ti, tj);
     const int bi = blockIdx.x;
     const bool diag_tile = ti == tj;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(256) csd_normalize_tiles_kernel(const float2* 
     if (tid < 160) {
         const bool col = tid >= 32;
         const int l = col ? tid - 32 : bi * 32 + tid;
-        const int tt = n_tiles == 1 ? 0 : ((col ? tj : ti) == 0 ? 0 : 2);
+        const int tt = tri_diag(nb, col ? tj : ti);
         const float2* __restrict__ dt = fbase + tt * (128 * 128) + l * 129;
         float2 d = make_float2(0.f, 0.f);
         for (int sidx = 0; sidx < n_src; ++sidx) { const float2 w = __ldg(dt + sidx * src_stride); d.x += w.x; d.y += w.y; }
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(256) csd_normalize_tiles_kernel(const float2* 
 template <int KIND>
 static int launch_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, float pre_scale, void* out,
                                   cudaStream_t stream) {
-    const int n_tiles = n_chan == 256 ? 3 : 1;
+    const int n_tiles = tri_tiles(n_chan / 128);
     const long long src_stride = (long long)n_freq * n_tiles * 128 * 128;
     dim3 grid(4, n_tiles, n_freq);
     csd_normalize_tiles_kernel<KIND><<<grid, 256, 0, stream>>>(reinterpret_cast<const float2*>(slots), n_src, src_stride,
@@ -420,7 +422,7 @@ static int launch_normalize_tiles(const void* slots, int n_src, int n_freq, int 
 int csd_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, float pre_scale, int out_kind,
                         void* out, cudaStream_t stream) {
     if (n_freq <= 0) return 0;
-    if (n_chan != 128 && n_chan != 256) return fail("tile slots exist for 128 or 256 channels only (got %d)", n_chan);
+    if (n_chan < 128 || n_chan > 512 || n_chan % 128) return fail("tile slots exist for 128, 256, 384 or 512 channels (got %d)", n_chan);
     if (n_src < 1) return fail("csd_normalize_tiles: need at least one source slot");
     if (n_freq > 65535) return fail("csd_normalize_tiles: more than 65535 frequencies per call are not supported");
     switch (out_kind) {

@@ -50,7 +50,8 @@ constexpr int TC_MAX_RANKS = 16;
 
 struct TcArgs {
     int n_rows, n_freq, n_chan;
-    int n_tiles;               // upper-triangular 128x128 tiles per frequency (1 or 3)
+    int n_tiles;               // upper-triangular 128x128 tiles per frequency: nb (nb + 1) / 2
+    int n_blk;                 // nb = n_chan / 128 (1..4)
     int chain_ksteps;          // pipeline stages (of TC_KC rows) accumulated in TMEM before the FP32 flush
     int store_mode;            // 0: per-thread row stores (debug), 1: shared-memory transposed, coalesced
     int rewrite_hi;            // 1: store rna_tf32(x) back as the hi operand; 0: let the MMA truncate x itself
@@ -222,9 +223,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
 //     tiles back to back in the order (0,0), (1,1), (0,1): both diagonals are known when the off-diagonal tile ends.
 // t encodes the tile: 0 -> (0,0), 1 -> (0,1), 2 -> (1,1).
 struct ItemIter {
-    int n_tiles, n_freq, f_rot, fused, count;
+    int n_tiles, n_blk, n_freq, f_rot, fused, count;
     __device__ __forceinline__ ItemIter(const TcArgs& a)
-        : n_tiles(a.n_tiles), n_freq(a.n_freq), f_rot(a.f_rot), fused(a.store_mode == 3) {
+        : n_tiles(a.n_tiles), n_blk(a.n_blk), n_freq(a.n_freq), f_rot(a.f_rot), fused(a.store_mode == 3) {
         if (fused) {
             const int mf = ((int)blockIdx.x < n_freq) ? (n_freq - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
             count = mf * n_tiles;
@@ -237,7 +238,15 @@ struct ItemIter {
         if (fused) {
             const int m = k / n_tiles, idx = k - m * n_tiles;
             f = (int)blockIdx.x + m * (int)gridDim.x;
-            t = n_tiles == 1 ? 0 : (idx == 0 ? 0 : (idx == 1 ? 2 : 1));
+            // all diagonal tiles first (their rsqrt feeds every off-diagonal tile), then the others in row-major order
+            if (idx < n_blk) {
+                t = tri_diag(n_blk, idx);
+            } else {
+                int rest = idx - n_blk;
+                int bi = 0;
+                while (rest >= n_blk - 1 - bi) { rest -= n_blk - 1 - bi; ++bi; }
+                t = tri_diag(n_blk, bi) + 1 + rest;
+            }
         } else {
             const int item = (int)blockIdx.x + k * (int)gridDim.x;
             const int fl = item / n_tiles;
@@ -245,8 +254,7 @@ struct ItemIter {
             f = fl + f_rot;
             if (f >= n_freq) f -= n_freq;
         }
-        ti = t >> 1;
-        tj = (t + 1) >> 1;
+        tri_decode(n_blk, t, ti, tj);
     }
 };
 
@@ -541,7 +549,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             float2* stg = staging + (warp - 8) * (32 * 16);
             const bool diag_tile = ti == tj;
             if (a.store_mode == 3) {
-                float* diag = reinterpret_cast<float*>(staging + 8 * 32 * 16);     // [2][128] rsqrt of the diagonal
+                float* diag = reinterpret_cast<float*>(staging + 8 * 32 * 16);     // [n_blk <= 4][128] rsqrt of the diagonal
                 const int r0 = lane_grp * 32, r_loc = r0 + lane, cb = chalf * 64;
                 if (diag_tile) {
                     float dv = 0.f;
@@ -734,13 +742,13 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 bool csd_tc_supported(int n_chan, long long sx_f, long long sx_r) {
-    return (n_chan == 128 || n_chan == 256) && sx_r % 4 == 0 && sx_f % 4 == 0;
+    return n_chan >= 128 && n_chan <= 512 && n_chan % 128 == 0 && sx_r % 4 == 0 && sx_f % 4 == 0;
 }
 
 static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     if (d.n_freq <= 0 || d.n_chan <= 0) return 0;
     if (!csd_tc_supported(d.n_chan, d.sx_f, d.sx_r))
-        return fail("tcgen05 CSD kernel needs n_chan in {128, 256} and 16-byte aligned strides "
+        return fail("tcgen05 CSD kernel needs n_chan in {128, 256, 384, 512} and 16-byte aligned strides "
                     "(got n_chan=%d, sx_f=%lld, sx_r=%lld)", d.n_chan, d.sx_f, d.sx_r);
     if (reinterpret_cast<uintptr_t>(d.planes) % 16 != 0)
         return fail("tcgen05 CSD kernel needs 16-byte aligned buffers");
@@ -760,7 +768,8 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code %d", (int)r);
 
     a.n_rows = d.n_rows; a.n_freq = d.n_freq; a.n_chan = C;
-    a.n_tiles = C == 256 ? 3 : 1;
+    a.n_blk = C / 128;
+    a.n_tiles = tri_tiles(a.n_blk);
     a.alpha = d.alpha; a.beta = d.beta;
     // accumulation-chain length in rows (multiple of TC_KC); SPYB_TC_CHAIN_ROWS overrides for experiments
     int chain_rows = 64;
@@ -772,8 +781,10 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     // cross terms as BF16 MMAs by default (1.1e-6 vs FP64, all-TF32: 1.3e-6); SPYB_TC_BF16=0 selects 3xTF32
     a.bf16_cross = 1;
     if (const char* e = getenv("SPYB_TC_BF16")) a.bf16_cross = atoi(e) != 0;
-    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2) +
-                        2 * 128 * sizeof(float);
+    // 896 bytes of slack reach the next 1024-byte boundary from any 128-byte aligned start (dynamic shared memory
+    // starts at least that aligned); 1024 would push the total 104 bytes past the 227 KB limit
+    const size_t smem = 896 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2) +
+                        4 * 128 * sizeof(float);
 
     // per device / context attribute: set on every launch (several engines may live in one process)
     SPYB_CUDA(cudaFuncSetAttribute(csd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -806,7 +817,7 @@ int csd_coherence_tc(const CsdPlanarDesc& d, int out_kind, void* out, cudaStream
     return launch_tc(d, a, stream);
 }
 
-int csd_tile_count(int n_chan) { return n_chan == 256 ? 3 : 1; }
+int csd_tile_count(int n_chan) { return tri_tiles((n_chan + 127) / 128); }
 
 int csd_accumulate_tc_tiles(const CsdPlanarDesc& d, void* const* owner_base, const int* f_begin, int n_owners,
                             int src_rank, cudaStream_t stream) {

@@ -157,3 +157,41 @@ def test_cfg2_full_size_vs_oracle(engine, taper, opt):
     dg = np.einsum("fii->fi", coh[0])
     assert np.abs(dg - 1).max() <= 1e-6
     assert coh.max() <= 1 + 1e-6
+
+
+@pytest.mark.parametrize("n_chan", [384, 512])
+@pytest.mark.parametrize("rows", [37, 200])
+def test_wide_channel_counts(engine, rows, n_chan):
+    """3 and 4 blocks of 128 channels (6 / 10 upper tiles): all three store modes against the float64 contraction"""
+    import torch
+    assert engine.csd_planar_supported(n_chan) and engine.csd_tile_count(n_chan) == (6 if n_chan == 384 else 10)
+    p, z = _planes(4, rows, n_chan, seed=rows + n_chan)
+    planes = torch.from_numpy(p).to(engine.tdev)
+    want = _f64_mean(z)
+    d = np.sqrt(np.abs(np.einsum("fii->fi", want)))
+    coh = want / (d[:, :, None] * d[:, None, :])
+    # full Hermitian matrix
+    got = engine.csd_accumulate_planar(planes, alpha=1.0 / rows).cpu().numpy()
+    assert np.array_equal(got, got.conj().transpose(0, 2, 1))
+    assert _per_freq_err(got, want) <= TOL and _per_freq_err(got, _oracle_mean(z)) <= TOL
+    # fused coherence
+    fused = engine.csd_coherence_planar(planes, output="fourier").cpu().numpy()
+    assert _per_freq_err(fused, coh) <= TOL
+    assert np.array_equal(engine.csd_coherence_planar(planes, output="abs").cpu().numpy(),
+                          engine.csd_coherence_planar(planes, output="abs").cpu().numpy().transpose(0, 2, 1))
+    # tile slots + normalisation
+    nt = engine.csd_tile_count(n_chan)
+    slots = torch.zeros((1, 4, nt, 128, 128), dtype=torch.complex64, device=engine.tdev)
+    engine.csd_accumulate_tiles(planes, [slots.data_ptr()], [0, 4], 0)
+    tiles = engine.csd_normalize_tiles(slots, n_chan, output="fourier", pre_scale=1.0).cpu().numpy()
+    assert _per_freq_err(tiles, coh) <= TOL
+    assert np.array_equal(tiles, tiles.conj().transpose(0, 2, 1))
+
+
+def test_batched_coherence_384_channels(engine):
+    from syncopy_b200 import batched
+    trials = synth.white_noise(6, 256, 384)
+    coh, freqs = batched.coherence(trials, 500., taper="hann", polyremoval=0, to_host=True)
+    av = oc.trial_average([oc.cross_spectra_cF(t.copy(), 500., taper="hann", polyremoval=0)[0] for t in trials])
+    assert coh.shape == (1, 129, 384, 384)
+    assert nerr(coh, oc.normalize_csd(av, "abs")) <= TOL

@@ -743,7 +743,22 @@ def run_gpu_arm(args):
     # ---- end to end through the public API (pinned host in, pinned host out) ---------------------
     coh_host = torch.empty(stepper.coh.shape, dtype=torch.float32).pin_memory()
 
+    # N = 1: through the batched compute_sequential stand-in (syncopy_b200.cr): the dataset is the host array
+    # [nSamplesTotal, nChannels] + trialdefinition, chunks travel through double-buffered pinned staging while the
+    # previous chunk is transformed.  N > 1: batched.coherence on the rank's shard (peer tile exchange).
+    from syncopy_b200 import cr
+    host2d = hnp.reshape(N_TRIALS * N_SAMPLES, N_CHAN)
+    trialdef = np.stack([np.arange(N_TRIALS) * N_SAMPLES, (np.arange(N_TRIALS) + 1) * N_SAMPLES,
+                         np.zeros(N_TRIALS, dtype=np.int64)], axis=1)
+    e2e_bytes = {}
+
     def e2e_step():
+        if world == 1 and args.csd_impl == 0:
+            res = cr.compute_sequential(host2d, trialdef, "coh", FS, keeptrials=False, taper=w["taper"],
+                                        taper_opt=w["taper_opt"], polyremoval=0, output="abs", engine=eng,
+                                        out_host=coh_host)
+            e2e_bytes.update(h2d=res["h2d_bytes"], d2h=res["d2h_bytes"])
+            return res["result"]
         c, _ = batched.coherence(host, FS, taper=w["taper"], taper_opt=w["taper_opt"], polyremoval=0,
                                  output="abs", engine=eng, impl={0: 0, 2: 0, 1: 1, 3: 1}[args.csd_impl],
                                  reduce_group=group, out_host=coh_host, gather=False)
@@ -851,7 +866,9 @@ def run_gpu_arm(args):
             "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": stepper.coh.numel() * 4, "steps": e2e_steps,
-                    "api": "syncopy_b200.batched.coherence(pinned host trials) -> pinned host coherence"},
+                    "api": ("syncopy_b200.cr.compute_sequential(host dataset [samples, channels] + trialdefinition, 'coh') "
+                            "-> pinned host coherence (chunked double-buffered pinned staging)") if world == 1 and
+                    args.csd_impl == 0 else "syncopy_b200.batched.coherence(pinned host trials) -> pinned host coherence"},
             "gpu_launches": int(launches_per_step * args.steps),
             "parity": parity,
             "roofline": roofline, "kernels": kernels, "hbm_pipeline": hbm_pipeline,

@@ -65,15 +65,43 @@ def _groups_by_length(layout, chunk_bytes):
     return chunks
 
 
+_STAGING = {}          # (device, kind) -> list of two reusable buffers; pinning memory costs ~0.1 s per GB
+
+
+def _staging(dev, kind, n_elems, dtype, pinned):
+    """Two grow-only staging buffers per device and purpose, reused across calls."""
+    key = (str(dev), kind, dtype)
+    bufs = _STAGING.get(key)
+    if bufs is None or bufs[0].numel() < n_elems:
+        if pinned:
+            bufs = [torch.empty(n_elems, dtype=dtype).pin_memory() for _ in range(2)]
+        else:
+            bufs = [torch.empty(n_elems, dtype=dtype, device=dev) for _ in range(2)]
+        _STAGING[key] = bufs
+    return bufs
+
+
+def _pinned_view(source):
+    """A torch view of `source` if it is host memory that CUDA can DMA from directly (pinned), else None."""
+    try:
+        t = source if isinstance(source, torch.Tensor) else (torch.from_numpy(source) if isinstance(source, np.ndarray) else None)
+        if t is not None and t.dtype == torch.float32 and not t.is_cuda and t.is_contiguous() and t.is_pinned():
+            return t
+    except Exception:      # noqa: BLE001  (memmaps, read-only arrays, h5py datasets: staged through pinned buffers)
+        pass
+    return None
+
+
 class _Pipeline:
     """Double-buffered pinned staging: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i."""
 
-    def __init__(self, eng, max_in_elems, max_out_elems, out_dtype):
+    def __init__(self, eng, max_in_elems, max_out_elems, out_dtype, source=None):
         self.eng = eng
         self.dev = eng.tdev
-        self.pin_in = [torch.empty(max_in_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.dev_in = [torch.empty(max_in_elems, dtype=torch.float32, device=self.dev) for _ in range(2)]
-        self.pin_out = [torch.empty(max_out_elems, dtype=out_dtype).pin_memory() for _ in range(2)] if max_out_elems else None
+        self.direct = _pinned_view(source)       # pinned source: DMA straight from it, no staging copy
+        self.pin_in = None if self.direct is not None else _staging(self.dev, "in", max_in_elems, torch.float32, True)
+        self.dev_in = _staging(self.dev, "dev", max_in_elems, torch.float32, False)
+        self.pin_out = _staging(self.dev, "out", max_out_elems, out_dtype, True) if max_out_elems else None
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.back_stream = torch.cuda.Stream(self.dev)
         self.h2d_done = [None, None]
@@ -86,12 +114,30 @@ class _Pipeline:
         """Pack trials ks (equal length n) into pinned buffer `slot`, start the H2D copy; returns the device view."""
         C = layout.n_chan
         nb = len(ks)
+        dst = self.dev_in[slot][: nb * n * C].view(nb, n, C)
+        if self.direct is not None:
+            # pinned source: one DMA per run of selection entries that are adjacent in the dataset
+            with torch.cuda.stream(self.copy_stream):
+                if self.in_free[slot] is not None:
+                    self.copy_stream.wait_event(self.in_free[slot])
+                i = 0
+                while i < nb:
+                    j = i + 1
+                    while j < nb and layout.source[ks[j]].start == layout.source[ks[j - 1]].stop:
+                        j += 1
+                    a, b = layout.source[ks[i]].start, layout.source[ks[j - 1]].stop
+                    dst[i:j].view(-1, C).copy_(self.direct[a:b], non_blocking=True)
+                    i = j
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            self.h2d_done[slot] = ev
+            self.h2d_bytes += nb * n * C * 4
+            return dst
         if self.h2d_done[slot] is not None:
             self.h2d_done[slot].synchronize()                # the pinned buffer is free again
         host = self.pin_in[slot][: nb * n * C].view(nb, n, C).numpy()
         for i, k in enumerate(ks):
             host[i] = source[layout.source[k], :]            # one read per (possibly repeated) selection entry
-        dst = self.dev_in[slot][: nb * n * C].view(nb, n, C)
         with torch.cuda.stream(self.copy_stream):
             if self.in_free[slot] is not None:
                 self.copy_stream.wait_event(self.in_free[slot])
@@ -215,7 +261,7 @@ def _spectral(eng, source, layout, method, samplerate, keeptrials, target, chunk
     if not keeptrials and len(set(rows)) > 1:
         raise NotImplementedError("Averaging trials of unequal lengths in output currently not supported!")
     lay, total = layout.stack(rows)
-    pipe = _Pipeline(eng, max_in, 0, dt)
+    pipe = _Pipeline(eng, max_in, 0, dt, source)
     freqs, acc, trailing = None, None, None
     pending = None                                # (slot, ks, pinned host view): D2H in flight
 
@@ -246,7 +292,7 @@ def _spectral(eng, source, layout, method, samplerate, keeptrials, target, chunk
                 elif tuple(target.shape) != shape:
                     raise ValueError(f"target has shape {tuple(target.shape)}, the results need {shape}")
                 per_chunk = max(len(k) * _rows_per_trial(method, m, cfg) for m, k in chunks) * int(np.prod(trailing))
-                pipe.pin_out = [torch.empty(per_chunk, dtype=dt).pin_memory() for _ in range(2)]
+                pipe.pin_out = _staging(pipe.dev, "out", per_chunk, dt, True)
         elif tuple(spec.shape[2:]) != trailing:
             raise ValueError("per-trial results disagree in their non-stacking dimensions")
         if not keeptrials:
@@ -301,9 +347,14 @@ def _cross_spectral(eng, source, layout, method, samplerate, keeptrials, target,
     chunks = _groups_by_length(layout, chunk_bytes)
     max_in = max(n * len(ks) for n, ks in chunks) * n_chan
     out_elems = n_freq * n_chan * n_chan if (method == "csd" and keeptrials) else 0
-    pipe = _Pipeline(eng, max_in, out_elems, torch.complex64)
+    pipe = _Pipeline(eng, max_in, out_elems, torch.complex64, source)
     max_rows = max(len(ks) for _, ks in chunks) * K
-    if use_tc:
+    # coherence on the tensor-core path with every row resident: the chunks' spectra fill one buffer and a single
+    # contraction with normalising epilogue finishes the job (no cross-spectral matrix in memory)
+    fused_coh = (method == "coh" and use_tc and n_total * per_trial_spec <= batched.MAX_SPECTRA_BYTES)
+    if fused_coh:
+        spectra = eng.scratch("cr_planar_spectra", (n_freq, n_total * K, 2, n_chan), torch.float32)
+    elif use_tc:
         spectra = eng.scratch("cr_planar_spectra", (n_freq, max_rows, 2, n_chan), torch.float32)
     else:
         spectra = eng.scratch("cr_spectra", (n_freq, max_rows, n_chan), torch.complex64)
@@ -316,6 +367,7 @@ def _cross_spectral(eng, source, layout, method, samplerate, keeptrials, target,
         elif tuple(target.shape) != shape:
             raise ValueError(f"target has shape {tuple(target.shape)}, the results need {shape}")
     pending = None
+    row0 = 0
     nxt = pipe.upload(0, source, layout, chunks[0][1], chunks[0][0])
     for ci, (n, ks) in enumerate(chunks):
         x = nxt
@@ -324,10 +376,16 @@ def _cross_spectral(eng, source, layout, method, samplerate, keeptrials, target,
             nxt = pipe.upload((ci + 1) % 2, source, layout, chunks[ci + 1][1], chunks[ci + 1][0])
         pipe.wait_upload(slot)
         tapers = eng.taper_table(taper, n, nfft, taper_opt)
-        view = spectra[:, : len(ks) * K]
+        if fused_coh:
+            view = spectra[:, row0: row0 + len(ks) * K]
+            row0 += len(ks) * K
+        else:
+            view = spectra[:, : len(ks) * K]
         eng.mtmfft(x, tapers, nfft, hm.mtmfft_scale(n, nfft), polyremoval=pr, demean_taper=demean, freq_idx=fidx,
                    output="fourier_planar" if use_tc else "fourier", keeptapers=True, out=view, freq_major=True)
         pipe.release_input(slot)
+        if fused_coh:
+            continue
         if method == "csd" and keeptrials:
             one = (eng.csd_accumulate_planar(view, alpha=1.0 / K) if use_tc
                    else eng.csd_accumulate(view, alpha=1.0 / K, impl=1))
@@ -349,6 +407,8 @@ def _cross_spectral(eng, source, layout, method, samplerate, keeptrials, target,
         return dict(result=target, layout=lay, freqs=freqs, meta=meta, h2d_bytes=pipe.h2d_bytes, d2h_bytes=pipe.d2h_bytes)
     if method == "csd":
         res = eng.scale_(acc, 1.0 / n_total)[None]
+    elif fused_coh:
+        res = eng.csd_coherence_planar(spectra, output=cfg.get("output", "abs"))[None]
     elif method == "coh":
         res = eng.csd_normalize(acc[None], output=cfg.get("output", "abs"), pre_scale=1.0 / n_total)
     else:

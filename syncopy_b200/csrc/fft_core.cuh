@@ -17,6 +17,7 @@
 // no twiddles).
 #pragma once
 #include "common.cuh"
+#include "packed.cuh"
 
 namespace spyb {
 
@@ -101,6 +102,31 @@ template <> struct Radix<16> {
     }
 };
 
+// Packed-FP32 versions (packed.cuh: one instruction per complex add, two per complex multiply) with the same
+// register conventions as Radix<R>::run above; used by the pass below.
+template <int R> struct RadixP;
+template <> struct RadixP<2> {
+    __device__ __forceinline__ static void run(c2 (&x)[2]) { const c2 t = x[0]; x[0] = add2(t, x[1]); x[1] = sub2(t, x[1]); }
+};
+template <> struct RadixP<4> {
+    __device__ __forceinline__ static void run(c2 (&x)[4]) { dft4(x[0], x[1], x[2], x[3]); }
+};
+template <> struct RadixP<8> {
+    __device__ __forceinline__ static void run(c2 (&x)[8]) {
+        dft4(x[0], x[2], x[4], x[6]);
+        dft4(x[1], x[3], x[5], x[7]);
+        const float h = 0.70710678118654752440f;
+        x[3] = mul2(add2(x[3], mul_mi(x[3])), bc(h));          // (1 - i)/sqrt2
+        x[5] = mul_mi(x[5]);                                   // -i
+        x[7] = mul2(sub2(mul_mi(x[7]), x[7]), bc(h));          // (-1 - i)/sqrt2
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const c2 t = x[2 * q]; x[2 * q] = add2(t, x[2 * q + 1]); x[2 * q + 1] = sub2(t, x[2 * q + 1]); }
+    }
+};
+template <> struct RadixP<16> {
+    __device__ __forceinline__ static void run(c2 (&x)[16]) { dft16(x); }
+};
+
 // ---------------------------------------------------------------------------------------
 // One Stockham pass: twiddle, E/R in-register DFTs, scatter into shared memory.
 // ---------------------------------------------------------------------------------------
@@ -113,17 +139,23 @@ __device__ __forceinline__ void fft_pass_scatter(float2 (&v)[16], float2* __rest
     for (int u = 0; u < U; ++u) {
         const int b = j + u * NT;
         const int k = b & (NS - 1);
-        float2 x[R];
+        c2 x[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[r] = v[u + r * U];
+        for (int r = 0; r < R; ++r) x[r] = pk(v[u + r * U].x, v[u + r * U].y);
         if (NS > 1) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) x[r] = cmul(x[r], __ldg(&tw[(r - 1) * NS + k]));
+            for (int r = 1; r < R; ++r) {
+                const float2 w = __ldg(&tw[(r - 1) * NS + k]);
+                x[r] = cmul2(x[r], w.x, w.y);
+            }
         }
-        Radix<R>::run(x);
+        RadixP<R>::run(x);
         const int j0 = (b - k) * R + k;
 #pragma unroll
-        for (int q = 0; q < R; ++q) s[fft_pad(j0 + q * NS) * P + p] = x[Radix<R>::reg_of(q)];
+        for (int q = 0; q < R; ++q) {
+            const c2 y = x[Radix<R>::reg_of(q)];
+            s[fft_pad(j0 + q * NS) * P + p] = make_float2(re(y), im(y));
+        }
     }
 }
 

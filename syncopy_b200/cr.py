@@ -84,7 +84,12 @@ def _staging(dev, kind, n_elems, dtype, pinned):
 def _pinned_view(source):
     """A torch view of `source` if it is host memory that CUDA can DMA from directly (pinned), else None."""
     try:
-        t = source if isinstance(source, torch.Tensor) else (torch.from_numpy(source) if isinstance(source, np.ndarray) else None)
+        if isinstance(source, torch.Tensor):
+            t = source
+        elif type(source) is np.ndarray and source.flags.writeable:     # (memmaps / read-only arrays are staged)
+            t = torch.from_numpy(source)
+        else:
+            t = None
         if t is not None and t.dtype == torch.float32 and not t.is_cuda and t.is_contiguous() and t.is_pinned():
             return t
     except Exception:      # noqa: BLE001  (memmaps, read-only arrays, h5py datasets: staged through pinned buffers)

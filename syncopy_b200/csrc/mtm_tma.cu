@@ -418,6 +418,11 @@ __global__ void __launch_bounds__(THREADS, 1) mtm_tma_kernel(const __grid_consta
             const long long off = off0 + (long long)kf * a.so_freq;
             if constexpr (PLANAR) {
                 float* op = reinterpret_cast<float*>(a.out) + off;
+                if (ta.dbg & 16) {          // experiment: streaming (evict-first) stores
+                    __stcs(reinterpret_cast<float4*>(op), make_float4(re(re0), im(re0), re(re1), im(re1)));
+                    __stcs(reinterpret_cast<float4*>(op + a.n_chan), make_float4(re(im0), im(im0), re(im1), im(im1)));
+                    return;
+                }
                 *reinterpret_cast<ulonglong2*>(op) = make_ulonglong2(re0, re1);
                 *reinterpret_cast<ulonglong2*>(op + a.n_chan) = make_ulonglong2(im0, im1);
             } else if (a.out_kind == OUT_FOURIER) {
@@ -517,13 +522,16 @@ int mtm_launch_tma(int log2n, const MtmArgs& a, cudaStream_t stream) {
     if (!encode) return -1;
 
     CUtensorMap tmap;
+    static const int promo = getenv("SPYB_MTM_L2PROMO") ? atoi(getenv("SPYB_MTM_L2PROMO")) : 2;
+    const CUtensorMapL2promotion l2promo = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE :
+                                           promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                                           promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     const cuuint64_t gdim[3] = {(cuuint64_t)a.n_chan, (cuuint64_t)a.n_samples, (cuuint64_t)a.n_trials};
     const cuuint64_t gstride[2] = {(cuuint64_t)a.n_chan * 4, (cuuint64_t)a.trial_stride * 4};
     const cuuint32_t box[3] = {8, (cuuint32_t)BLK_ROWS, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.x), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (mtm input) failed with code %d", (int)r);
 
     TmaArgs ta;

@@ -73,8 +73,6 @@ class TileExchange:
         self.f_begin = freq_slabs(self.n_freq, self.world)
         self.nf_local = self.f_begin[self.rank + 1] - self.f_begin[self.rank]
         self.call = 0
-        self._side = None                 # second stream for `normalize(overlap=True)`
-        self._norm_done = None            # event: the overlapped normalisation of the previous call has finished
         shape = (self.world, max(self.nf_local, 1), self.n_tiles, 128, 128)
         nbytes = int(np.prod(shape)) * 8
         lib = engine.lib
@@ -115,11 +113,6 @@ class TileExchange:
         counts completes.  Returns the global trial count; when the caller already knows it (`n_total`) the
         result is not read back, so the host never waits for the device.
         """
-        if self._norm_done is not None:
-            # an overlapped normalisation still reads the buffer that the call after this one overwrites: nobody may
-            # pass this barrier before it is done
-            torch.cuda.current_stream(self.eng.tdev).wait_event(self._norm_done)
-            self._norm_done = None
         if self.world > 1:
             if getattr(self, "_cnt", None) is None:
                 self._cnt = torch.empty(1, dtype=torch.float64, device=self.eng.tdev)
@@ -131,40 +124,16 @@ class TileExchange:
             n_total = n_trials
         return n_total
 
-    def normalize(self, n_total, output="abs", out=None, overlap=False):
-        """
-        Sum over the source ranks + coherency of the local slab [nF_slab, C, C]; ends the current call.
-        `overlap=True` (needs a caller-owned `out`): the kernel runs on a second stream behind the barrier, so in a
-        sequence of calls it overlaps the tapered FFT and the contraction of the NEXT call (which fill the other slot
-        buffer); the result is complete once that stream -- or the next call's barrier -- has been waited for
-        (`wait_normalized`).
-        """
+    def normalize(self, n_total, output="abs", out=None):
+        """Sum over the source ranks + coherency of the local slab [nF_slab, C, C]; ends the current call.
+        (Running this kernel on a second stream under the next call's FFT was tried and measured slower at N = 2:
+        1.72 -> 1.84 ms per step, the persistent FFT blocks and the normalisation compete for SMs and HBM.)"""
         k = self.call % 2
         self.call += 1
         if self.nf_local == 0:
             return torch.empty((0, self.n_chan, self.n_chan), device=self.eng.tdev)
-        if not overlap:
-            return self.eng.csd_normalize_tiles(self.slots[k][:, :self.nf_local], self.n_chan, output=output,
-                                                pre_scale=1.0 / n_total, out=out)
-        assert out is not None, "overlapped normalisation writes into a caller-owned buffer"
-        main = torch.cuda.current_stream(self.eng.tdev)
-        if self._side is None:
-            self._side = torch.cuda.Stream(self.eng.tdev)
-        ready = torch.cuda.Event()
-        ready.record(main)
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(ready)
-            res = self.eng.csd_normalize_tiles(self.slots[k][:, :self.nf_local], self.n_chan, output=output,
-                                               pre_scale=1.0 / n_total, out=out)
-            done = torch.cuda.Event()
-            done.record(self._side)
-        self._norm_done = done
-        return res
-
-    def wait_normalized(self):
-        """Make the current stream wait for an overlapped normalisation (no-op otherwise)."""
-        if self._norm_done is not None:
-            torch.cuda.current_stream(self.eng.tdev).wait_event(self._norm_done)
+        return self.eng.csd_normalize_tiles(self.slots[k][:, :self.nf_local], self.n_chan, output=output,
+                                            pre_scale=1.0 / n_total, out=out)
 
     def finish(self, n_trials, output="abs", out=None, n_total=None):
         n_total = self.barrier(n_trials, n_total)

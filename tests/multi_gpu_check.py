@@ -62,6 +62,39 @@ def main():
     good = e_g <= 1e-3 and bool(meta["converged--bool"]) == bool(meta1["converged--bool"])
     ok = ok and good
     print(f"[rank {rank}] granger (all-reduce path): {e_g:.1e} {'ok' if good else 'MISMATCH'}", flush=True)
+    # sharded Wilson, same CSD on every rank: == the single-rank factorisation to rounding (stage-wise check: the
+    # factorisation amplifies differences of the CSD sums, not of its own arithmetic)
+    from syncopy_b200.distributed import WilsonExchange
+    torch.manual_seed(7)
+    nF, C = 65, 6
+    A = torch.randn((nF, C, C), dtype=torch.complex128, device=eng.tdev)
+    S = A @ A.conj().transpose(1, 2) + 0.5 * torch.eye(C, dtype=torch.complex128, device=eng.tdev)
+    S[0] = S[0].real.to(torch.complex128)
+    S[-1] = S[-1].real.to(torch.complex128)
+    wx = WilsonExchange(eng, nF, dist.group.WORLD)
+    H, Sig, conv, err, it = eng.wilson_sf(S, n_iter=60, rtol=1e-10, slab=wx.slab, exchange=wx)
+    H1, Sig1, conv1, err1, it1 = eng.wilson_sf(S, n_iter=60, rtol=1e-10)
+    lo, hi = wx.slab
+    e_h = ((H[lo:hi] - H1[lo:hi]).abs().max() / H1.abs().max()).item() if hi > lo else 0.0
+    e_s = ((Sig - Sig1).abs().max() / Sig1.abs().max()).item()
+    good = e_h <= 1e-9 and e_s <= 1e-9 and it == it1 and conv == conv1
+    ok = ok and good
+    print(f"[rank {rank}] sharded Wilson vs single rank: H {e_h:.1e} Sigma {e_s:.1e} iterations {it}/{it1} "
+          f"{'ok' if good else 'MISMATCH'}", flush=True)
+    # a matrix that is not positive definite at ONE frequency (owned by the last rank only): every rank must raise,
+    # nobody may be left waiting in a collective (the flag is max-reduced through the exchange callback)
+    from syncopy_b200 import _lib
+    Sbad = S.clone()
+    Sbad[nF - 2] = -Sbad[nF - 2]
+    raised = False
+    try:
+        eng.wilson_sf(Sbad, n_iter=5, rtol=1e-10, slab=wx.slab, exchange=wx)
+    except _lib.SpybError as exc:
+        raised = True
+        msg = str(exc)
+    ok = ok and raised
+    print(f"[rank {rank}] non-positive-definite slab on the last rank: {'raised: ' + msg[:70] if raised else 'NOT RAISED'}",
+          flush=True)
     flag = torch.tensor([0.0 if ok else 1.0], device=eng.tdev)
     dist.all_reduce(flag)
     dist.destroy_process_group()

@@ -32,7 +32,8 @@ int spyb_version(void);
 int spyb_init(int device);                 /* cudaSetDevice + warm-up of the context       */
 const char* spyb_last_error(void);
 long long spyb_launch_count(void);         /* number of kernels this library has launched  */
-int spyb_max_fft_len(int pow2);            /* largest supported length (pow2 / arbitrary)  */
+int spyb_max_fft_len(int pow2);            /* longest transform of the shared-memory kernels (pow2 / arbitrary);
+                                              longer ones (up to 2^24) run as global-memory passes           */
 
 /*
  * (Multi-)tapered FFT of whole trials.
@@ -170,8 +171,8 @@ int spyb_detrend(const float* x, int n_trials, long long trial_stride, int n_sam
  *   xspec   complex64 [n_trials][n_dft/2+1][n_chan]: one-sided FFT_{n_dft} of the zero-padded (detrended) trials,
  *           as spyb_mtmfft writes it with a unit taper, scale 1 and nfft = n_dft
  *   kern    complex64 [n_scales][max_fac][n_dft] = FFT_{n_dft}(h_{s,j}) / n_dft with h[d mod n_dft] = psi[d + (M-1)/2]
- *           (psi sampled by the caller in float64 exactly as the reference does; n_dft a power of two <= 16384,
- *           >= n_samples + the kernel's half support)
+ *           (psi sampled by the caller in float64 exactly as the reference does; n_dft a power of two <= 16384 or
+ *           any even length with prime factors <= 61 beyond that, >= n_samples + the kernel's half support)
  *   expo    float32 [n_scales][max_fac] exponents (principal-branch complex power; 1 = none)
  *   n_fac   int32 [n_scales] number of factors in use
  *   out     [n_trials][n_time][n_scales][n_chan] float32 or complex64 by out_kind; rows n = 0 .. n_time-1

@@ -321,10 +321,11 @@ __global__ void __launch_bounds__(256) csd_normalize_tiles_kernel(const float2* 
     __shared__ float2 s_t[32][33];
     __shared__ int s_general;
     const int t = blockIdx.y, f = blockIdx.z;
-    const int nb = C / 128;
+    const int nb = (C + 127) / 128;                              // the last block may be zero padding (C % 32 == 0)
     int ti, tj;
     tri_decode(nb, t, ti, tj);
     const int bi = blockIdx.x;
+    if (ti * 128 + bi * 32 >= C) return;                         // padding rows (block-uniform)
     const bool diag_tile = ti == tj;
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const float2* __restrict__ fbase = slots + (long long)f * n_tiles * (128 * 128);
@@ -341,7 +342,8 @@ __global__ void __launch_bounds__(256) csd_normalize_tiles_kernel(const float2* 
         d.x *= pre_scale; d.y *= pre_scale;
         const float rs = rsqrtf(d.x);
         if (col) { s_dj[tid - 32] = d; s_rj[tid - 32] = rs; } else { s_di[tid] = d; s_ri[tid] = rs; }
-        if (d.y != 0.f || !(d.x > 0.f)) s_general = 1;
+        const int gl = (col ? tj : ti) * 128 + l;                // padding channels have a zero diagonal: not a reason
+        if (gl < C && (d.y != 0.f || !(d.x > 0.f))) s_general = 1;   // for the general (complex-sqrt) path
     }
     __syncthreads();
     const bool general = s_general != 0;
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(256) csd_normalize_tiles_kernel(const float2* 
     for (int bj = diag_tile ? bi : 0; bj < 4; ++bj) {            // chunks left of the diagonal are never read
         const bool diag_blk = diag_tile && bi == bj;
         const int J0 = tj * 128 + bj * 32;
+        if (J0 >= C) break;                                      // padding columns
         float2 v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = make_float2(0.f, 0.f);
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(256) csd_normalize_tiles_kernel(const float2* 
 template <int KIND>
 static int launch_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, float pre_scale, void* out,
                                   cudaStream_t stream) {
-    const int n_tiles = tri_tiles(n_chan / 128);
+    const int n_tiles = tri_tiles((n_chan + 127) / 128);
     const long long src_stride = (long long)n_freq * n_tiles * 128 * 128;
     dim3 grid(4, n_tiles, n_freq);
     csd_normalize_tiles_kernel<KIND><<<grid, 256, 0, stream>>>(reinterpret_cast<const float2*>(slots), n_src, src_stride,
@@ -422,7 +425,7 @@ static int launch_normalize_tiles(const void* slots, int n_src, int n_freq, int 
 int csd_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, float pre_scale, int out_kind,
                         void* out, cudaStream_t stream) {
     if (n_freq <= 0) return 0;
-    if (n_chan < 128 || n_chan > 512 || n_chan % 128) return fail("tile slots exist for 128, 256, 384 or 512 channels (got %d)", n_chan);
+    if (n_chan < 64 || n_chan > 512 || n_chan % 32) return fail("tile slots exist for 64..512 channels in multiples of 32 (got %d)", n_chan);
     if (n_src < 1) return fail("csd_normalize_tiles: need at least one source slot");
     if (n_freq > 65535) return fail("csd_normalize_tiles: more than 65535 frequencies per call are not supported");
     switch (out_kind) {

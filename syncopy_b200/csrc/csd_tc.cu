@@ -51,7 +51,7 @@ constexpr int TC_MAX_RANKS = 16;
 struct TcArgs {
     int n_rows, n_freq, n_chan;
     int n_tiles;               // upper-triangular 128x128 tiles per frequency: nb (nb + 1) / 2
-    int n_blk;                 // nb = n_chan / 128 (1..4)
+    int n_blk;                 // nb = ceil(n_chan / 128) (1..4); the last block may be zero-padded
     int chain_ksteps;          // pipeline stages (of TC_KC rows) accumulated in TMEM before the FP32 flush
     int store_mode;            // 0: per-thread row stores (debug), 1: shared-memory transposed, coalesced
     int rewrite_hi;            // 1: store rna_tf32(x) back as the hi operand; 0: let the MMA truncate x itself
@@ -563,6 +563,10 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 const float* __restrict__ dj = diag + tj * 128 + cb;
                 const int kind = a.out_kind;
                 const size_t row_dir = 0;
+                // channel counts that are not multiples of 128 (but of 32): rows / columns >= C of the last block are
+                // zero padding (TMA out-of-bounds fill); a warp's 32 rows and every 16- or 32-column chunk are valid
+                // or padding as a whole, so the guards are warp-uniform
+                if (ti * 128 + r0 >= C) continue;
                 // Pointers walk with one add per element and the triangle tests are predicates on plain stores: the
                 // epilogue has ~16 us per tile before it holds up the MMAs, and only two warps per scheduler.
                 auto store_real = [&](auto diag_tag, auto kind_tag) {
@@ -573,6 +577,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
 #pragma unroll
                     for (int c0 = 0; c0 < 64; c0 += 32) {
                         if (DG && cb + c0 + 31 < r0) continue;                   // entirely below the diagonal
+                        if (tj * 128 + cb + c0 >= C) continue;                   // padding columns
                         float* pm = outf + (size_t)(tj * 128 + cb + c0) * C + ti * 128 + r_loc;   // mirrored (j, i)
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) {
@@ -607,6 +612,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
 #pragma unroll
                     for (int c0 = 0; c0 < 64; c0 += 16) {
                         if (diag_tile && cb + c0 + 15 < r0) continue;            // entirely below the diagonal
+                        if (tj * 128 + cb + c0 >= C) continue;                   // padding columns
                         float2* pm = outc + (size_t)(tj * 128 + cb + c0) * C + ti * 128 + r_loc;
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) {
@@ -671,9 +677,11 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             }
             if (a.store_mode == 0) {
                 float2* __restrict__ orow = fmat + (size_t)i * C;
+                if (i >= C) continue;                            // padding rows
 #pragma unroll
                 for (int c = 0; c < 64; ++c) {
                     const int j = jb + c;
+                    if (j >= C) continue;                        // padding columns
                     if (diag_tile && j < i) continue;
                     float2 o = make_float2(sr[c] * a.alpha, si[c] * a.alpha);
                     if (a.beta != 0.f) {
@@ -686,9 +694,11 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 }
                 continue;
             }
+            if (i0 >= C) continue;                               // padding rows (warp-uniform: C % 32 == 0)
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 if (diag_tile && jb + c0 + 15 < i0) continue;    // chunk entirely below the diagonal (warp-uniform)
+                if (jb + c0 >= C) continue;                      // padding columns
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
                     const int j = jb + c0 + jj;
@@ -742,13 +752,13 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 bool csd_tc_supported(int n_chan, long long sx_f, long long sx_r) {
-    return n_chan >= 128 && n_chan <= 512 && n_chan % 128 == 0 && sx_r % 4 == 0 && sx_f % 4 == 0;
+    return n_chan >= 64 && n_chan <= 512 && n_chan % 32 == 0 && sx_r % 4 == 0 && sx_f % 4 == 0;
 }
 
 static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     if (d.n_freq <= 0 || d.n_chan <= 0) return 0;
     if (!csd_tc_supported(d.n_chan, d.sx_f, d.sx_r))
-        return fail("tcgen05 CSD kernel needs n_chan in {128, 256, 384, 512} and 16-byte aligned strides "
+        return fail("tcgen05 CSD kernel needs 64 <= n_chan <= 512, a multiple of 32, and 16-byte aligned strides "
                     "(got n_chan=%d, sx_f=%lld, sx_r=%lld)", d.n_chan, d.sx_f, d.sx_r);
     if (reinterpret_cast<uintptr_t>(d.planes) % 16 != 0)
         return fail("tcgen05 CSD kernel needs 16-byte aligned buffers");
@@ -768,7 +778,7 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code %d", (int)r);
 
     a.n_rows = d.n_rows; a.n_freq = d.n_freq; a.n_chan = C;
-    a.n_blk = C / 128;
+    a.n_blk = (C + 127) / 128;          // boxes reaching past C are zero-filled by TMA
     a.n_tiles = tri_tiles(a.n_blk);
     a.alpha = d.alpha; a.beta = d.beta;
     // accumulation-chain length in rows (multiple of TC_KC); SPYB_TC_CHAIN_ROWS overrides for experiments

@@ -202,6 +202,9 @@ static int launch_cwt(const CwtArgs& a, bool need_acc, cudaStream_t stream) {
 
 int cwt_factors(const CwtDesc& d, cudaStream_t stream) {
     if (d.n_trials <= 0 || d.n_chan <= 0 || d.n_scales <= 0 || d.n_time <= 0) return 0;
+    if (d.n_time > d.n_dft) return fail("cwt: n_time (%d) exceeds the transform length (%d)", d.n_time, d.n_dft);
+    if (d.max_fac < 1) return fail("cwt: need at least one factor per scale");
+    if (d.n_dft > 16384) return cwt_factors_long(d, stream);          // beyond the shared-memory kernel
     if (d.n_dft < 16 || (d.n_dft & (d.n_dft - 1))) return fail("cwt: transform length must be a power of two >= 16");
     if (d.n_time > d.n_dft) return fail("cwt: n_time (%d) exceeds the transform length (%d)", d.n_time, d.n_dft);
     if (d.max_fac < 1) return fail("cwt: need at least one factor per scale");

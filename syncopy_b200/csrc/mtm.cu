@@ -321,6 +321,7 @@ int mtm_frames(const MtmFramesDesc& d, cudaStream_t stream) {
     if (d.n_trials <= 0 || d.n_frames <= 0 || d.n_chan <= 0 || d.n_freq_out <= 0) return 0;
     if (d.n_win < 1 || d.n_win > d.n_dft) return fail("window length %d must be in [1, nfft=%d]", d.n_win, d.n_dft);
     if (d.n_tapers < 1) return fail("need at least one taper");
+    if (mtm_needs_long(d.n_dft)) return mtm_frames_long(d, stream);     // beyond the shared-memory kernels
     const FftPlan* pl = get_fft_plan(d.n_dft);
     if (!pl) return 1;
 

@@ -26,6 +26,9 @@ struct MtmFramesDesc {
     float* chan_amax = nullptr;
 };
 int mtm_frames(const MtmFramesDesc& d, cudaStream_t stream);
+// fft_long.cu: transform lengths beyond the shared-memory kernels (global-memory Stockham passes, Bluestein)
+bool mtm_needs_long(int n_dft);
+int mtm_frames_long(const MtmFramesDesc& d, cudaStream_t stream);
 
 // Cross-spectral contraction acc = beta*acc + alpha * sum_r X_r X_r^H per frequency (csd.cu)
 struct CsdDesc {
@@ -72,6 +75,7 @@ struct CwtDesc {
     void* out = nullptr;             // device [trial][n_time][scale][chan]
 };
 int cwt_factors(const CwtDesc& d, cudaStream_t stream);
+int cwt_factors_long(const CwtDesc& d, cudaStream_t stream);   // fft_long.cu: circular length > 16384
 int transpose2d(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t stream);
 int detrend(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, int polyremoval,
             float* out, long long out_trial_stride, cudaStream_t stream);

@@ -20,6 +20,7 @@ from . import hostmath as hm
 MAX_TABLES = 64
 MAX_PLANS = 8
 MAX_LAUNCH_DIM = 65535                      # CUDA grid.y / grid.z limit of one launch
+MAX_LONG_FFT = 1 << 24                      # longest transform of the global-memory FFT path (csrc/fft_long.cu)
 
 _CDTYPE = {True: torch.complex64, False: torch.float32}
 
@@ -326,10 +327,8 @@ class Engine:
         def make():
             flat = [t for tl in taps_per_scale for t in tl]
             L = hm.conv_same_length(n_samples, flat)
-            if L > self.lib.spyb_max_fft_len(1):
-                raise _lib.SpybError(
-                    f"wavelet transform of {n_samples} samples needs a circular length of {L} > "
-                    f"{self.lib.spyb_max_fft_len(1)} (the shared-memory FFT engine's limit)")
+            if L > MAX_LONG_FFT:
+                raise _lib.SpybError(f"transform of {n_samples} samples needs a circular length of {L} > {MAX_LONG_FFT}")
             nS = len(taps_per_scale)
             max_fac = max(len(tl) for tl in taps_per_scale)
             kern = np.zeros((nS, max_fac, L), dtype=np.complex64)
@@ -360,6 +359,12 @@ class Engine:
         if out is None:
             out = torch.empty((B, N, nS, Cn), dtype=dt, device=self.tdev)
         assert out.is_contiguous() and out.dtype == dt and tuple(out.shape) == (B, N, nS, Cn)
+        if L > self.lib.spyb_max_fft_len(1):
+            # global-memory path (csrc/fft_long.cu): columns = (scale, channel), reference layouts on both sides
+            _lib.check(self.lib.spyb_cwt(xspec.data_ptr(), B, Cn, L, plan["kern"].data_ptr(), plan["expo"].data_ptr(),
+                                         plan["nfac"].data_ptr(), nS, plan["max_fac"], N, kind, 0, out.data_ptr(),
+                                         self.stream()))
+            return out
         # the transform kernel owns one channel of one scale per block: feed it channel-major spectra and let it
         # write time-contiguous rows, then transpose into the reference layout [time][scale][channel]
         nF = L // 2 + 1
@@ -536,9 +541,8 @@ class Engine:
         L = 16
         while L < 2 * N - 1:
             L *= 2
-        if L > self.lib.spyb_max_fft_len(1):
-            raise _lib.SpybError(f"cross-covariance of {N} samples needs a circular length of {L} > "
-                                 f"{self.lib.spyb_max_fft_len(1)} (the shared-memory FFT engine's limit)")
+        if L > MAX_LONG_FFT:
+            raise _lib.SpybError(f"cross-covariance of {N} samples needs a circular length of {L} > {MAX_LONG_FFT}")
         ones = self._cached(self._lru, MAX_TABLES, ("ones", N), lambda: torch.ones((1, N), dtype=torch.float32, device=self.tdev))
         xspec = self.mtmfft(x[None], ones, L, 1.0, polyremoval=polyremoval, output="fourier", keeptapers=True)  # [1,1,nF,C]
         nF = L // 2 + 1

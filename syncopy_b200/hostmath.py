@@ -209,8 +209,12 @@ def superlet_factors(scales, order_max, order_min=1, c_1=3, adaptive=False):
     return factors
 
 
+SMEM_FFT_MAX = 16384          # longest transform of the shared-memory FFT kernels (spyb_max_fft_len(1))
+
+
 def conv_same_length(n_samples, taps_list):
-    """Smallest power-of-two circular length that reproduces fftconvolve(x, taps, 'same') for every kernel."""
+    """Smallest supported circular length (power of two; 5-smooth beyond the shared-memory kernels) that reproduces
+    fftconvolve(x, taps, 'same') for every kernel."""
     need = 16
     for taps in taps_list:
         M = len(taps)
@@ -219,6 +223,21 @@ def conv_same_length(n_samples, taps_list):
     L = 16
     while L < need:
         L <<= 1
+    if L > SMEM_FFT_MAX:
+        # beyond the shared-memory kernels the global-memory FFT takes any 5-smooth length: the smallest
+        # 2^a 3^b 5^c >= need with a >= 4 (radix-16 passes first) instead of the next power of two
+        best = L
+        p5 = 1
+        while p5 < best:
+            p35 = p5
+            while p35 < best:
+                v = p35 * 16
+                while v < need:
+                    v <<= 1
+                best = min(best, v)
+                p35 *= 3
+            p5 *= 5
+        L = best
     return L
 
 

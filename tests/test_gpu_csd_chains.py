@@ -159,12 +159,15 @@ def test_cfg2_full_size_vs_oracle(engine, taper, opt):
     assert coh.max() <= 1 + 1e-6
 
 
-@pytest.mark.parametrize("n_chan", [384, 512])
+@pytest.mark.parametrize("n_chan", [64, 96, 192, 320, 384, 512])
 @pytest.mark.parametrize("rows", [37, 200])
 def test_wide_channel_counts(engine, rows, n_chan):
-    """3 and 4 blocks of 128 channels (6 / 10 upper tiles): all three store modes against the float64 contraction"""
+    """1 to 4 blocks of 128 channels (1 / 3 / 6 / 10 upper tiles), the last block zero-padded when the channel count
+    is not a multiple of 128 (64, 96, 192, 320): all three store modes against the float64 contraction"""
     import torch
-    assert engine.csd_planar_supported(n_chan) and engine.csd_tile_count(n_chan) == (6 if n_chan == 384 else 10)
+    nb = (n_chan + 127) // 128
+    assert engine.csd_planar_supported(n_chan) and engine.csd_tile_count(n_chan) == nb * (nb + 1) // 2
+    assert not engine.csd_planar_supported(48) and not engine.csd_planar_supported(200)
     p, z = _planes(4, rows, n_chan, seed=rows + n_chan)
     planes = torch.from_numpy(p).to(engine.tdev)
     want = _f64_mean(z)
@@ -188,10 +191,13 @@ def test_wide_channel_counts(engine, rows, n_chan):
     assert np.array_equal(tiles, tiles.conj().transpose(0, 2, 1))
 
 
-def test_batched_coherence_384_channels(engine):
+@pytest.mark.parametrize("n_chan", [192, 384])
+def test_batched_coherence_wide(engine, n_chan):
     from syncopy_b200 import batched
-    trials = synth.white_noise(6, 256, 384)
+    trials = synth.white_noise(6, 256, n_chan)
     coh, freqs = batched.coherence(trials, 500., taper="hann", polyremoval=0, to_host=True)
     av = oc.trial_average([oc.cross_spectra_cF(t.copy(), 500., taper="hann", polyremoval=0)[0] for t in trials])
-    assert coh.shape == (1, 129, 384, 384)
+    assert coh.shape == (1, 129, n_chan, n_chan)
     assert nerr(coh, oc.normalize_csd(av, "abs")) <= TOL
+    # padded tiles must not leak into the result buffer: a second, differently sized call reuses cached buffers
+    assert np.isfinite(coh).all()

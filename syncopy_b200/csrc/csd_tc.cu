@@ -52,6 +52,7 @@ struct TcArgs {
     int n_rows, n_freq, n_chan;
     int n_tiles;               // upper-triangular 128x128 tiles per frequency: nb (nb + 1) / 2
     int n_blk;                 // nb = ceil(n_chan / 128) (1..4); the last block may be zero-padded
+    int dbg;                   // SPYB_TC_DBG: 1 = skip the result stores (timing experiments only)
     int chain_ksteps;          // pipeline stages (of TC_KC rows) accumulated in TMEM before the FP32 flush
     int store_mode;            // 0: per-thread row stores (debug), 1: shared-memory transposed, coalesced
     int rewrite_hi;            // 1: store rna_tf32(x) back as the hi operand; 0: let the MMA truncate x itself
@@ -538,6 +539,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 tc_fence_before();
                 mbar_arrive(&acc_empty[buf]);
             }
+            if (a.dbg & 1) continue;
             // ---- store: elements on / above the diagonal as they are, plus their conjugates mirrored below it;
             // nothing computed below the diagonal is used, so the result is exactly Hermitian.  A thread owns a
             // row, so the mirrored stores (fixed j, lanes = consecutive i) coalesce as they are; the direct ones
@@ -793,6 +795,8 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     if (const char* e = getenv("SPYB_TC_REWRITE_HI")) a.rewrite_hi = atoi(e) != 0;
     // cross terms as BF16 MMAs by default (1.1e-6 vs FP64, all-TF32: 1.3e-6); SPYB_TC_BF16=0 selects 3xTF32
     a.bf16_cross = 1;
+    a.dbg = 0;
+    if (const char* e = getenv("SPYB_TC_DBG")) a.dbg = atoi(e);
     if (const char* e = getenv("SPYB_TC_BF16")) a.bf16_cross = atoi(e) != 0;
     // 896 bytes of slack reach the next 1024-byte boundary from any 128-byte aligned start (dynamic shared memory
     // starts at least that aligned); 1024 would push the total 104 bytes past the 227 KB limit

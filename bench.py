@@ -691,6 +691,14 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    # several ranks on one node: every process next to its own GPU (pinned buffers, copy threads); a single rank
+    # keeps all host cores for the CPU baseline leg
+    numa = {}
+    if world > 1:
+        from syncopy_b200.distributed import bind_to_gpu_numa
+        numa = bind_to_gpu_numa(local_rank)
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)           # every rank calls this, right after the rendezvous
     eng = get_engine(local_rank)
     dev = eng.tdev
     w = workload_cfg(args.taper)
@@ -869,6 +877,12 @@ def run_gpu_arm(args):
                     "api": ("syncopy_b200.cr.compute_sequential(host dataset [samples, channels] + trialdefinition, 'coh') "
                             "-> pinned host coherence (chunked double-buffered pinned staging)") if world == 1 and
                     args.csd_impl == 0 else "syncopy_b200.batched.coherence(pinned host trials) -> pinned host coherence"},
+            "host_binding": ({"per_rank": numa_all,
+                              "how": ("each rank pinned to the CPUs of its GPU's NUMA node before allocating its pinned "
+                                      "buffers (syncopy_b200.distributed.bind_to_gpu_numa)"
+                                      if any(n.get("bound") for n in numa_all) else
+                                      "not bound: sysfs reports no NUMA node for the GPUs on this box (single-node guest)")}
+                             if world > 1 else None),
             "gpu_launches": int(launches_per_step * args.steps),
             "parity": parity,
             "roofline": roofline, "kernels": kernels, "hbm_pipeline": hbm_pipeline,

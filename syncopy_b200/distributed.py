@@ -16,6 +16,52 @@ import torch
 import torch.distributed as dist
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device):
+    """NUMA node of a CUDA device from sysfs (None when the platform does not say)."""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        return node if node >= 0 else None
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        return None
+
+
+def bind_to_gpu_numa(device):
+    """
+    Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers it
+    allocates afterwards (first touch) and the copy threads live next to the GPU's PCIe root.  With one process per
+    GPU and every process on socket 0, half of the ranks of a two-socket box push their H2D traffic over the
+    inter-socket link.  Returns a dict describing what was done (empty when nothing could be done).
+    """
+    node = gpu_numa_node(device)
+    if node is None:
+        return {}
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = _parse_cpulist(fh.read())
+        import os
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        if not target:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, target)
+        return {"numa_node": node, "bound": True, "cpus": len(target)}
+    except (OSError, AttributeError, ValueError):
+        return {"numa_node": node, "bound": False}
+
+
 def trial_shard(n_trials, rank, world):
     """Contiguous block [lo, hi) of the (selection-ordered) trial list owned by `rank`."""
     base, rem = divmod(n_trials, world)

@@ -91,3 +91,15 @@ def test_wilson_exchange_rows_partition_the_circle():
                     for i in range(a, b):
                         owner[i] += 1
             assert owner == [1] * length, (n_freq, world)
+
+
+def test_numa_binding_helpers_are_safe_without_a_gpu():
+    """`bind_to_gpu_numa` must never raise: no CUDA device / no sysfs entry -> nothing bound, affinity unchanged."""
+    import os
+    from syncopy_b200 import distributed as d
+    assert d._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert d._parse_cpulist("5") == {5} and d._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = d.bind_to_gpu_numa(0)
+    assert isinstance(info, dict) and not info.get("bound", False)
+    assert os.sched_getaffinity(0) == before

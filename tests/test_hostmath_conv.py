@@ -77,3 +77,24 @@ def test_conv_same_length_is_minimal_power_of_two():
         c0 = (m - 1) // 2
         need = n + max(min(c0, n - 1), min(m - 1 - c0, n - 1))
         assert L >= need and (L & (L - 1)) == 0 and (L // 2 < need or L == 16)
+
+
+def test_conv_same_length_beyond_the_shared_memory_limit():
+    """power of two up to 16384; the smallest 5-smooth multiple of 16 beyond (global-memory FFT path)"""
+    import numpy as np
+    from syncopy_b200 import hostmath as hm
+    assert hm.conv_same_length(8192, [np.zeros(98)]) == 16384
+    for n, m in [(20000, 4001), (18000, 301), (100000, 10001), (16385, 3)]:
+        L = hm.conv_same_length(n, [np.zeros(m)])
+        c0 = (m - 1) // 2
+        assert L >= n + max(c0, m - 1 - c0) and L % 16 == 0
+        r = L
+        for f in (2, 3, 5):
+            while r % f == 0:
+                r //= f
+        assert r == 1
+        p2 = 16
+        while p2 < L:
+            p2 *= 2
+        assert L <= p2
+    assert hm.conv_same_length(20000, [np.zeros(4001)]) == 23040

@@ -70,9 +70,14 @@ def config_dict(args, n_gpus):
                     f"foi=None (2049 bins), output=abs, keeptrials=False",
         "trials_per_gpu": N_TRIALS, "n_channels": N_CHAN, "n_samples": N_SAMPLES, "n_tapers": w["K"],
         "parallelism": f"trial-sharded x{n_gpus}" + (
+            "; exchange fused into the tcgen05 contraction: tiles of the frequencies a rank does not own are stored "
+            "straight into the owner's slot buffer over NVLink P2P, counter all-reduce as barrier, then every rank "
+            "contracts its own frequency slab and adds the peers' tiles in the normalising epilogue; result left "
+            "sharded by frequency slab"
+            if n_gpus > 1 and getattr(args, "csd_impl", 0) == 0 else
             "; upper CSD tiles stored straight into the frequency-slab owner's slot buffer over NVLink P2P from the "
-            "tcgen05 epilogue, counter all-reduce as barrier, result left sharded by frequency slab"
-            if n_gpus > 1 and getattr(args, "csd_impl", 0) in (0, 2) else
+            "tcgen05 epilogue, counter all-reduce as barrier, per-slab normalisation kernel"
+            if n_gpus > 1 and getattr(args, "csd_impl", 0) == 2 else
             (" + NCCL all-reduce of the CSD sum" if n_gpus > 1 else "")),
         "l2_policy": "inputs (839 MB/step) and spectra exceed the 126 MB L2; no explicit flush",
     }
@@ -430,6 +435,10 @@ class Cfg2Step:
             self.mode = "simt"
         # one rank: the contraction's epilogue normalises and mirrors itself (K2 + K3 in one kernel)
         self.fused = self.mode == "tiles" and world == 1 and args.csd_impl == 0
+        # several ranks: the exchange fused into the contraction on both sides -- peers' frequencies as tiles over
+        # NVLink (K2a), barrier, own frequencies with the peers' tiles added in the normalising epilogue (K2b);
+        # --csd-impl 2 keeps the older tiles + barrier + normalisation kernel (K3) sequence
+        self.fused_exchange = self.mode == "tiles" and world > 1 and args.csd_impl == 0
         if self.mode == "tiles":
             from syncopy_b200.distributed import get_tile_exchange
             self.ex = get_tile_exchange(eng, self.n_freq, N_CHAN, group)
@@ -459,6 +468,15 @@ class Cfg2Step:
             eng.csd_coherence_planar(self.spectra, output="abs", out=self.coh[0])
             for i in (2, 3, 4):
                 rec(i)
+            return
+        if self.fused_exchange:
+            self.ex.accumulate_others(self.spectra)
+            rec(2)
+            self.ex.barrier(self.n_local, n_total=self.total_trials)   # counter all-reduce: every rank's tiles landed
+            rec(3)
+            self.ex.finish_fused(self.spectra, self.n_local, output="abs", out=self.coh[0], n_total=self.total_trials,
+                                 barrier=False)
+            rec(4)
             return
         if self.mode == "tiles":
             self.ex.accumulate(self.spectra, alpha=1.0 / K, beta=0.0)
@@ -742,10 +760,13 @@ def run_gpu_arm(args):
         sf, sc_, sb, sn = s_seg.mean(axis=0)
         strong = {"total_trials": N_TRIALS, "trials_per_gpu": hi - lo, "ms_per_step": s_ms / args.steps,
                   "value": N_TRIALS * args.steps / (s_ms * 1e-3), "unit": UNIT, "scaling": "strong",
-                  "kernels_ms": {"mtmfft (K1)": float(sf), "csd (K2)": float(sc_), "barrier": float(sb),
-                                 "normalize (K3)": float(sn)},
-                  "note": "fixed total work: the per-rank kernels shrink with N while the exchange barrier and the "
-                          "per-slab normalisation do not -- SURVEY 8e's caveat"}
+                  "kernels_ms": ({"mtmfft (K1)": float(sf), "csd others -> tiles (K2a)": float(sc_),
+                                  "barrier": float(sb), "csd own slab + peers' tiles, fused (K2b)": float(sn)}
+                                 if s_step.fused_exchange else
+                                 {"mtmfft (K1)": float(sf), "csd (K2)": float(sc_), "barrier": float(sb),
+                                  "normalize (K3)": float(sn)}),
+                  "note": "fixed total work: the per-rank FFT shrinks with N, the contraction's per-frequency "
+                          "epilogues and the exchange barrier do not -- SURVEY 8e's caveat"}
         del s_step
 
     # ---- end to end through the public API (pinned host in, pinned host out) ---------------------
@@ -804,7 +825,11 @@ def run_gpu_arm(args):
 
     if rank == 0:
         mode, fused, nf_local = stepper.mode, stepper.fused, stepper.nf_local
+        fused_x = stepper.fused_exchange
         fft_ms, csd_ms, ar_ms, norm_ms = seg.mean(axis=0)
+        k2a_ms, k2b_ms = csd_ms, norm_ms
+        if fused_x:                      # the contraction is split around the barrier: K2 = K2a + K2b, no K3
+            csd_ms, norm_ms = k2a_ms + k2b_ms, 0.0
         in_bytes = N_TRIALS * N_SAMPLES * N_CHAN * 4
         spec_bytes = n_freq * N_TRIALS * K * N_CHAN * 8
         csd_bytes = n_freq * N_CHAN * N_CHAN * 8
@@ -852,6 +877,16 @@ def run_gpu_arm(args):
             "normalize (K3)": {"ms": float(norm_ms), "bound": "hbm",
                                "achieved_gbs": k3_bytes / max(norm_ms, 1e-9) / 1e6},
         }
+        if fused_x:
+            del kernels["normalize (K3)"]
+            kernels["csd (K2)"]["ms_others_tiles_K2a"] = float(k2a_ms)
+            kernels["csd (K2)"]["ms_own_slab_fused_K2b"] = float(k2b_ms)
+            kernels["csd (K2)"]["bytes_gbs"] = (spec_bytes + csd_bytes * tile_frac * (world - 1) / world * 2
+                                                + 4 * nf_local * N_CHAN * N_CHAN) / (csd_ms * 1e-3) / 1e9
+            kernels["csd (K2)"]["fused"] = ("K2a: frequencies of the other ranks, upper tiles stored into the owners' slot "
+                                            "buffers over NVLink P2P; barrier; K2b: own frequency slab, the peers' tiles "
+                                            "added in the epilogue, then normalisation + mirror -- no reduction or "
+                                            "normalisation kernel")
         if fused:       # K2's epilogue normalises: one kernel, coherence written once (4 B per element)
             del kernels["barrier"], kernels["normalize (K3)"]
             kernels["csd (K2)"]["bytes_gbs"] = (spec_bytes + csd_bytes / 2) / (csd_ms * 1e-3) / 1e9

@@ -99,7 +99,7 @@ int spyb_csd_accumulate(const void* spectra, long long sx_f, long long sx_r, int
  *   planes   float32 "planar" spectra as written by spyb_mtmfft with out_kind = 8:
  *            element (f, r, plane, c) at f*sx_f + r*sx_r + plane*n_chan + c, plane 0 = real, 1 = imaginary
  *   acc      complex64 [n_freq][n_chan][n_chan], acc = beta*acc + alpha * sum_r X_r X_r^H
- * spyb_csd_planar_supported() tells whether a shape is eligible (n_chan in {128, 256}, strides % 4 == 0);
+ * spyb_csd_planar_supported() tells whether a shape is eligible (64 <= n_chan <= 512 in multiples of 32, strides % 4 == 0);
  * ineligible shapes go through spyb_csd_accumulate.
  */
 int spyb_csd_planar_supported(int n_chan, long long sx_f, long long sx_r);
@@ -136,6 +136,22 @@ int spyb_csd_accumulate_tiles(const float* planes, long long sx_f, long long sx_
                               const int* f_begin_host, int n_owners, int src_rank, void* stream);
 int spyb_csd_normalize_tiles(const void* slots, int n_src, int n_freq_local, int n_chan, float pre_scale,
                              int out_kind, void* out, void* stream);
+/*
+ * Several ranks, all rows of a rank in one launch: the exchange fused into the contraction on both sides.
+ * spyb_csd_accumulate_tiles_others is spyb_csd_accumulate_tiles without the frequencies rank src_rank owns itself;
+ * after the barrier spyb_csd_coherence_planar_slots runs those (planes / n_freq = the local slab) like
+ * spyb_csd_coherence_planar, its epilogue adding the tiles the peers stored into the local slot buffer
+ * slots [n_src][n_freq][n_tiles][128][128] (source skip_src = this rank is not read) before it normalises: the
+ * trial sum over ranks (computational_routine.py:1022-1032, the reference's locked HDF5 "+=",
+ * shared/kwarg_decorators.py:722-735) and csd.py:118-172 without a separate reduction or normalisation kernel.
+ * The peers must have used alpha = 1 (coherency does not depend on a common factor).
+ */
+int spyb_csd_accumulate_tiles_others(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                                     int n_chan, float alpha, float beta, void* const* owner_base_host,
+                                     const int* f_begin_host, int n_owners, int src_rank, void* stream);
+int spyb_csd_coherence_planar_slots(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                                    int n_chan, const void* slots, int n_src, int skip_src, int out_kind, void* out,
+                                    void* stream);
 
 /*
  * Slot buffers that other ranks of the node can write into (one process per GPU): plain cudaMalloc memory plus

@@ -40,6 +40,8 @@ PROTOTYPES = {
     "spyb_csd_tile_count": (_i, [_i]),
     "spyb_csd_coherence_planar": (_i, [_vp, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
     "spyb_csd_accumulate_tiles": (_i, [_vp, _ll, _ll, _i, _i, _i, _f, _f, C.POINTER(C.c_void_p), _ip, _i, _i, _vp]),
+    "spyb_csd_accumulate_tiles_others": (_i, [_vp, _ll, _ll, _i, _i, _i, _f, _f, C.POINTER(C.c_void_p), _ip, _i, _i, _vp]),
+    "spyb_csd_coherence_planar_slots": (_i, [_vp, _ll, _ll, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "spyb_csd_normalize_tiles": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp]),
     "spyb_peer_alloc": (_i, [_ll, C.POINTER(C.c_void_p), C.c_char_p]),
     "spyb_peer_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),

@@ -257,29 +257,48 @@ def _coherence_tiles(eng, trials, samplerate, nSamples, foi, taper, taper_opt, p
         coh = eng.csd_coherence_planar(spectra, output=output)
         return _finish(coh[None], to_host, out_host), freqs
     ex = get_tile_exchange(eng, n_freq, n_chan, reduce_group)
+    lo, hi = ex.f_begin[ex.rank], ex.f_begin[ex.rank + 1]
+    if ex.world > 1 and chunk >= B and not os.environ.get("SPYB_NO_FUSED_EXCHANGE"):
+        # several ranks, all rows of the rank in one launch: the exchange is fused into the contraction on both
+        # sides (peers' frequencies as tiles over NVLink, barrier, own slab with the peers' tiles added in the
+        # normalising epilogue) -- no reduction or normalisation kernel
+        eng.mtmfft(x, tapers, nfft, scale, polyremoval=pr, freq_idx=fidx, output="fourier_planar",
+                   keeptapers=True, out=spectra, freq_major=True)
+        ex.accumulate_others(spectra)
+        coh, _ = ex.finish_fused(spectra, B, output=output)
+        if not gather:
+            return _finish(coh[None], to_host, out_host), freqs[lo:hi]
+        return _finish(_gather_slabs(eng, ex, coh, reduce_group), to_host, out_host), freqs
     for b0 in range(0, B, chunk):
         nb = min(chunk, B - b0)
         view = spectra[:, :nb * K]
         eng.mtmfft(x[b0:b0 + nb], tapers, nfft, scale, polyremoval=pr, freq_idx=fidx, output="fourier_planar",
                    keeptapers=True, out=view, freq_major=True)
-        ex.accumulate(view, alpha=1.0 / K, beta=0.0 if b0 == 0 else 1.0)
-    lo, hi = ex.f_begin[ex.rank], ex.f_begin[ex.rank + 1]
+        # alpha = 1 on every rank (coherency does not depend on a common factor): a rank whose shard needs several
+        # chunks stays compatible with peers that took the fused route above
+        ex.accumulate(view, alpha=1.0, beta=0.0 if b0 == 0 else 1.0)
     if ex.world == 1 or not gather:
         out_dev = None
         coh, _ = ex.finish(B, output=output, out=out_dev)
         return _finish(coh[None], to_host, out_host), freqs[lo:hi]
-    # every rank wants the whole result: all-gather the normalised slabs (padded to the largest slab)
     coh, _ = ex.finish(B, output=output)
+    return _finish(_gather_slabs(eng, ex, coh, reduce_group), to_host, out_host), freqs
+
+
+def _gather_slabs(eng, ex, coh, group):
+    """Every rank wants the whole result: all-gather the normalised slabs (padded to the largest slab)."""
+    import torch.distributed as dist
+    lo, hi = ex.f_begin[ex.rank], ex.f_begin[ex.rank + 1]
+    n_chan = ex.n_chan
     nf_max = max(ex.f_begin[r + 1] - ex.f_begin[r] for r in range(ex.world))
     pad = torch.zeros((nf_max, n_chan, n_chan), dtype=coh.dtype, device=eng.tdev)
     pad[:hi - lo] = coh
     full = torch.empty((ex.world, nf_max, n_chan, n_chan), dtype=coh.dtype, device=eng.tdev)
     if coh.dtype == torch.complex64:
-        dist.all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(pad), group=reduce_group)
+        dist.all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(pad), group=group)
     else:
-        dist.all_gather_into_tensor(full, pad, group=reduce_group)
-    res = torch.cat([full[r, :ex.f_begin[r + 1] - ex.f_begin[r]] for r in range(ex.world)], dim=0)[None]
-    return _finish(res, to_host, out_host), freqs
+        dist.all_gather_into_tensor(full, pad, group=group)
+    return torch.cat([full[r, :ex.f_begin[r + 1] - ex.f_begin[r]] for r in range(ex.world)], dim=0)[None]
 
 
 def n_chan_of(csd):

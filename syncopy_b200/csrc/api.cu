@@ -128,8 +128,31 @@ int spyb_csd_accumulate_tiles(const float* planes, long long sx_f, long long sx_
     d.planes = planes; d.sx_f = sx_f; d.sx_r = sx_r;
     d.n_rows = n_rows; d.n_freq = n_freq; d.n_chan = n_chan;
     d.alpha = alpha; d.beta = beta; d.acc = nullptr;
-    return csd_accumulate_tc_tiles(d, owner_base_host, f_begin_host, n_owners, src_rank,
+    return csd_accumulate_tc_tiles(d, owner_base_host, f_begin_host, n_owners, src_rank, 0,
                                    static_cast<cudaStream_t>(stream));
+}
+
+int spyb_csd_accumulate_tiles_others(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                                     int n_chan, float alpha, float beta, void* const* owner_base_host,
+                                     const int* f_begin_host, int n_owners, int src_rank, void* stream) {
+    if (!owner_base_host || !f_begin_host) return fail("owner_base_host / f_begin_host must not be NULL");
+    CsdPlanarDesc d;
+    d.planes = planes; d.sx_f = sx_f; d.sx_r = sx_r;
+    d.n_rows = n_rows; d.n_freq = n_freq; d.n_chan = n_chan;
+    d.alpha = alpha; d.beta = beta; d.acc = nullptr;
+    return csd_accumulate_tc_tiles(d, owner_base_host, f_begin_host, n_owners, src_rank, 1,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int spyb_csd_coherence_planar_slots(const float* planes, long long sx_f, long long sx_r, int n_rows, int n_freq,
+                                    int n_chan, const void* slots, int n_src, int skip_src, int out_kind, void* out,
+                                    void* stream) {
+    if (out_kind < 0 || out_kind > 7) return fail("bad out_kind %d", out_kind);
+    CsdPlanarDesc d;
+    d.planes = planes; d.sx_f = sx_f; d.sx_r = sx_r;
+    d.n_rows = n_rows; d.n_freq = n_freq; d.n_chan = n_chan;
+    d.alpha = 1.f; d.beta = 0.f; d.acc = nullptr;
+    return csd_coherence_tc_slots(d, slots, n_src, skip_src, out_kind, out, static_cast<cudaStream_t>(stream));
 }
 
 int spyb_csd_normalize_tiles(const void* slots, int n_src, int n_freq_local, int n_chan, float pre_scale,

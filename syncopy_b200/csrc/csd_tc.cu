@@ -66,6 +66,12 @@ struct TcArgs {
     int f_begin[TC_MAX_RANKS + 1];
     int n_owners, src_rank;
     int f_rot;                 // first frequency this rank works on (0 outside tile-slot mode)
+    int n_freq_work;           // tile-slot mode: frequencies processed from f_rot on (wrapping); n_freq = all,
+                               // fewer = the slab of this rank itself is left to the fused launch below
+    // store_mode 3 on several ranks: the launch covers the frequencies this rank owns and the epilogue adds the
+    // tiles its peers stored into the local slot buffer [n_src][n_freq][n_tiles][128][128] before normalising
+    const float2* add_base;
+    int n_add_src, add_skip;
     // store_mode 3 ("fused coherence", one rank, all rows in one launch): the epilogue normalises with the
     // diagonal and writes the converted coherency [n_freq][C][C] (float32, or complex64 for out_kind 2) including
     // the mirrored half; the cross-spectral matrix itself never reaches memory (csd.py:118-172 fused into the sum)
@@ -231,7 +237,7 @@ struct ItemIter {
             const int mf = ((int)blockIdx.x < n_freq) ? (n_freq - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
             count = mf * n_tiles;
         } else {
-            const int n_items = n_freq * n_tiles;
+            const int n_items = a.n_freq_work * n_tiles;
             count = ((int)blockIdx.x < n_items) ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
         }
     }
@@ -519,6 +525,32 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             float sr[64], si[64];
 #pragma unroll
             for (int c = 0; c < 64; ++c) { sr[c] = 0.f; si[c] = 0.f; }
+            if (a.store_mode == 3 && a.n_add_src > 0) {
+                // Several ranks: the running sums start from the partial sums of the other ranks (tile-slot layout,
+                // written by their store_mode 2 launches) instead of zero -- this thread's row, its 64 columns = 512
+                // contiguous bytes per source.  Issued before the first chain is waited for, so the loads fly while
+                // the tensor core works on this tile.  Fixed order -> deterministic.
+                const int r0 = (warp & 3) * 32, r_loc = r0 + lane, cb = ((warp - 8) >> 2) * 64;
+                const bool diag_tile = ti == tj;
+                for (int src = 0; src < a.n_add_src; ++src) {
+                    if (src == a.add_skip) continue;
+                    const float4* __restrict__ prow = reinterpret_cast<const float4*>(
+                        a.add_base + (((size_t)src * a.n_freq + f) * a.n_tiles + t) * (128 * 128) + (size_t)r_loc * 128 + cb);
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                        // pieces entirely below the diagonal are never written by the producer (nor used here)
+                        if (diag_tile && cb + c0 + 15 < r0) continue;
+                        float4 v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = __ldcs(prow + c0 / 2 + q);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            sr[c0 + 2 * q] += v[q].x; si[c0 + 2 * q] += v[q].y;
+                            sr[c0 + 2 * q + 1] += v[q].z; si[c0 + 2 * q + 1] += v[q].w;
+                        }
+                    }
+                }
+            }
             for (int k0 = 0; k0 < n_ksteps; k0 += chain_ksteps, ++chain) {
                 const uint32_t buf = chain & 1u;
                 mbar_wait(&acc_full[buf], (chain >> 1) & 1u);
@@ -808,7 +840,8 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     int dev = 0, n_sm = 148;
     SPYB_CUDA(cudaGetDevice(&dev));
     SPYB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int n_items = a.store_mode == 3 ? d.n_freq : d.n_freq * a.n_tiles;
+    if (a.store_mode != 2 || a.n_freq_work <= 0 || a.n_freq_work > d.n_freq) a.n_freq_work = d.n_freq;
+    const int n_items = a.store_mode == 3 ? d.n_freq : a.n_freq_work * a.n_tiles;
     const int grid = n_items < n_sm ? n_items : n_sm;
     csd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, a);
     SPYB_LAUNCH_CHECK("csd_tc_kernel");
@@ -834,10 +867,29 @@ int csd_coherence_tc(const CsdPlanarDesc& d, int out_kind, void* out, cudaStream
     return launch_tc(d, a, stream);
 }
 
+// Fused coherence of the frequencies this rank owns on several ranks: `d` covers the local slab, `slots` is the local
+// slot buffer [n_src][d.n_freq][n_tiles][128][128] the peers filled (store_mode 2 with skip_own); source `skip_src`
+// (this rank) is not read -- its contribution is the contraction of this launch.
+int csd_coherence_tc_slots(const CsdPlanarDesc& d, const void* slots, int n_src, int skip_src, int out_kind, void* out,
+                           cudaStream_t stream) {
+    if (reinterpret_cast<uintptr_t>(out) % 16 != 0 || reinterpret_cast<uintptr_t>(slots) % 16 != 0)
+        return fail("tcgen05 CSD kernel needs 16-byte aligned buffers");
+    if (n_src < 1 || n_src > TC_MAX_RANKS) return fail("tile slots: 1..%d source ranks supported (got %d)", TC_MAX_RANKS, n_src);
+    if (slots == nullptr) return fail("tile slots: no slot buffer");
+    TcArgs a = {};
+    a.store_mode = 3;
+    a.coh_out = out;
+    a.out_kind = out_kind;
+    a.add_base = static_cast<const float2*>(slots);
+    a.n_add_src = n_src;
+    a.add_skip = skip_src;
+    return launch_tc(d, a, stream);
+}
+
 int csd_tile_count(int n_chan) { return tri_tiles((n_chan + 127) / 128); }
 
 int csd_accumulate_tc_tiles(const CsdPlanarDesc& d, void* const* owner_base, const int* f_begin, int n_owners,
-                            int src_rank, cudaStream_t stream) {
+                            int src_rank, int skip_own, cudaStream_t stream) {
     if (n_owners < 1 || n_owners > TC_MAX_RANKS) return fail("tile slots: 1..%d owner ranks supported (got %d)", TC_MAX_RANKS, n_owners);
     if (src_rank < 0) return fail("tile slots: bad source rank %d", src_rank);
     if (f_begin[0] != 0 || f_begin[n_owners] != d.n_freq) return fail("tile slots: frequency slabs must cover [0, %d)", d.n_freq);
@@ -853,6 +905,13 @@ int csd_accumulate_tc_tiles(const CsdPlanarDesc& d, void* const* owner_base, con
     }
     a.f_begin[n_owners] = f_begin[n_owners];
     a.f_rot = n_owners > 1 ? f_begin[(src_rank + 1) % n_owners] % d.n_freq : 0;
+    a.n_freq_work = d.n_freq;
+    if (skip_own) {
+        // the frequencies this rank owns are left out: it runs them itself in fused mode (csd_coherence_tc_slots)
+        if (src_rank >= n_owners) return fail("tile slots: source rank %d owns no slab", src_rank);
+        a.n_freq_work = d.n_freq - (f_begin[src_rank + 1] - f_begin[src_rank]);
+        if (a.n_freq_work <= 0) return 0;
+    }
     return launch_tc(d, a, stream);
 }
 

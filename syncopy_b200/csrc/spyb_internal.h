@@ -59,7 +59,9 @@ int csd_accumulate_tc(const CsdPlanarDesc& d, cudaStream_t stream);
 int csd_coherence_tc(const CsdPlanarDesc& d, int out_kind, void* out, cudaStream_t stream);
 int csd_tile_count(int n_chan);
 int csd_accumulate_tc_tiles(const CsdPlanarDesc& d, void* const* owner_base, const int* f_begin, int n_owners,
-                            int src_rank, cudaStream_t stream);
+                            int src_rank, int skip_own, cudaStream_t stream);
+int csd_coherence_tc_slots(const CsdPlanarDesc& d, const void* slots, int n_src, int skip_src, int out_kind, void* out,
+                           cudaStream_t stream);
 int csd_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, float pre_scale, int out_kind,
                         void* out, cudaStream_t stream);
 // Wavelet / superlet transforms as FFT convolutions (cwt.cu)

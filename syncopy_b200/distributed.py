@@ -153,6 +153,29 @@ class TileExchange:
         k = self.call % 2
         self.eng.csd_accumulate_tiles(planes, self.owner_ptrs[k], self.f_begin, self.rank, alpha, beta)
 
+    def accumulate_others(self, planes):
+        """First half of the fused exchange: this rank's rows contracted for every frequency it does NOT own,
+        tiles stored straight into the owners' slot buffers (all rows of the rank in this one call)."""
+        k = self.call % 2
+        self.eng.csd_accumulate_tiles(planes, self.owner_ptrs[k], self.f_begin, self.rank, 1.0, 0.0, skip_own=True)
+
+    def finish_fused(self, planes, n_trials, output="abs", out=None, n_total=None, barrier=True):
+        """
+        Second half: barrier, then the frequencies this rank owns -- contraction of its own rows, the peers' tiles
+        added in the epilogue, normalised, converted and mirrored by the same kernel.  No reduction or
+        normalisation kernel, the summed cross-spectral matrix never exists in memory.  Ends the current call.
+        """
+        if barrier:                      # False: the caller has already passed `barrier()` for this call
+            n_total = self.barrier(n_trials, n_total)
+        k = self.call % 2
+        self.call += 1
+        if self.nf_local == 0:
+            return torch.empty((0, self.n_chan, self.n_chan), device=self.eng.tdev), n_total
+        f0, f1 = self.f_begin[self.rank], self.f_begin[self.rank + 1]
+        coh = self.eng.csd_coherence_planar(planes[f0:f1], output=output, out=out,
+                                            add_slots=self.slots[k][:, :self.nf_local], skip_src=self.rank)
+        return coh, n_total
+
     def barrier(self, n_trials, n_total=None):
         """
         All ranks have finished writing the current buffer once this (stream-ordered) all-reduce of the trial

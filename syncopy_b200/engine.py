@@ -248,11 +248,13 @@ class Engine:
     def csd_tile_count(self, n_chan):
         return int(self.lib.spyb_csd_tile_count(int(n_chan)))
 
-    def csd_accumulate_tiles(self, planes, owner_ptrs, f_begin, src_rank=0, alpha=1.0, beta=0.0):
+    def csd_accumulate_tiles(self, planes, owner_ptrs, f_begin, src_rank=0, alpha=1.0, beta=0.0, skip_own=False):
         """
         planes [nF, R, 2, C] float32 -> the upper 128x128 tiles of sum_r X_r X_r^H, frequency f written into the
         slot buffer of the rank owning f: `owner_ptrs[o]` is the (possibly peer-mapped) device address of rank o's
         buffer [n_src, f_begin[o+1]-f_begin[o], n_tiles, 128, 128] complex64, this rank fills source slot `src_rank`.
+        `skip_own`: leave out the frequencies `src_rank` owns itself (they go through `csd_coherence_planar`
+        with `add_slots` after the barrier).
         """
         import ctypes as C
         assert planes.is_cuda and planes.dtype == torch.float32 and planes.dim() == 4 and planes.shape[2] == 2
@@ -261,14 +263,16 @@ class Engine:
         n_own = len(owner_ptrs)
         ptrs = (C.c_void_p * n_own)(*[int(p) for p in owner_ptrs])
         fb = (C.c_int * (n_own + 1))(*[int(v) for v in f_begin])
-        _lib.check(self.lib.spyb_csd_accumulate_tiles(
-            planes.data_ptr(), (planes.stride(0) if nF > 1 else 2 * R * Cn), 2 * Cn, R, nF, Cn,
-            float(alpha), float(beta), ptrs, fb, n_own, int(src_rank), self.stream()))
+        fn = self.lib.spyb_csd_accumulate_tiles_others if skip_own else self.lib.spyb_csd_accumulate_tiles
+        _lib.check(fn(planes.data_ptr(), (planes.stride(0) if nF > 1 else 2 * R * Cn), 2 * Cn, R, nF, Cn,
+                      float(alpha), float(beta), ptrs, fb, n_own, int(src_rank), self.stream()))
 
-    def csd_coherence_planar(self, planes, output="abs", out=None):
+    def csd_coherence_planar(self, planes, output="abs", out=None, add_slots=None, skip_src=-1):
         """
         planes [nF, R, 2, C] float32 with ALL (trial, taper) rows -> coherency [nF, C, C] in one kernel: tcgen05
         contraction whose epilogue normalises, converts and mirrors (no cross-spectral matrix in memory).
+        `add_slots` [n_src, nF, n_tiles, 128, 128] complex64: partial sums of other ranks for the same nF
+        frequencies (tile-slot layout), added before the normalisation; source `skip_src` is not read.
         """
         assert planes.is_cuda and planes.dtype == torch.float32 and planes.dim() == 4 and planes.shape[2] == 2
         nF, R, _, Cn = planes.shape
@@ -277,9 +281,16 @@ class Engine:
         if out is None:
             out = torch.empty((nF, Cn, Cn), dtype=_CDTYPE[kind == 2], device=self.tdev)
         assert out.is_contiguous() and out.numel() == nF * Cn * Cn and out.dtype == _CDTYPE[kind == 2]
+        sx_f = planes.stride(0) if nF > 1 else 2 * R * Cn
+        if add_slots is not None:
+            assert add_slots.is_cuda and add_slots.dtype == torch.complex64 and add_slots.is_contiguous()
+            assert tuple(add_slots.shape[1:]) == (nF, self.csd_tile_count(Cn), 128, 128)
+            _lib.check(self.lib.spyb_csd_coherence_planar_slots(
+                planes.data_ptr(), sx_f, 2 * Cn, R, nF, Cn, add_slots.data_ptr(), int(add_slots.shape[0]),
+                int(skip_src), kind, out.data_ptr(), self.stream()))
+            return out
         _lib.check(self.lib.spyb_csd_coherence_planar(
-            planes.data_ptr(), (planes.stride(0) if nF > 1 else 2 * R * Cn), 2 * Cn, R, nF, Cn, kind,
-            out.data_ptr(), self.stream()))
+            planes.data_ptr(), sx_f, 2 * Cn, R, nF, Cn, kind, out.data_ptr(), self.stream()))
         return out
 
     def csd_normalize_tiles(self, slots, n_chan, output="abs", pre_scale=1.0, out=None):

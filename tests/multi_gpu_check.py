@@ -4,8 +4,9 @@ Multi-GPU parity script (run under torchrun, one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 
 Every rank takes its contiguous shard of the same seeded trials; the sharded coherence (tile stores into the
-frequency-slab owners over NVLink P2P, counter all-reduce as barrier, per-slab normalisation) must equal the
-single-rank result over all trials, both gathered and as per-rank slabs, and agree with the all-reduce path.
+frequency-slab owners over NVLink P2P, counter all-reduce as barrier, own slab contracted with the peers' tiles
+added in the normalising epilogue -- or the older per-slab normalisation kernel) must equal the single-rank result
+over all trials, both gathered and as per-rank slabs, and agree with the all-reduce path.
 Exit code 0 = parity holds on every rank.
 """
 import os
@@ -30,6 +31,9 @@ def main():
     eng = get_engine(local)
     ok = True
     for n_chan, n_trials, n_samples, taper, opt in [(256, 13, 512, "hann", None),
+                                                     (256, 300, 256, "hann", None),      # several accumulation chains
+                                                     (384, 11, 256, "hann", None),       # 3 channel blocks, 6 upper tiles
+                                                     (160, 7, 256, "hann", None),        # zero-padded last block
                                                      (128, 9, 300, "dpss", {"NW": 2, "Kmax": 3})]:
         trials = synth.white_noise(n_trials, n_samples, n_chan)
         lo, hi = trial_shard(n_trials, rank, world)
@@ -42,15 +46,29 @@ def main():
             ref, _ = batched.coherence(trials, 1000., output=output, **kw)          # all trials on this rank
             allred, _ = batched.coherence(trials[lo:hi], 1000., output=output, reduce_group=dist.group.WORLD,
                                           impl=1, **kw)                            # CUDA-core kernel + all-reduce
+            # the older sequence (all tiles -> barrier -> per-slab normalisation kernel) and a mixed group (odd
+            # ranks fused, even ranks not: what happens when only some shards need several chunks)
+            os.environ["SPYB_NO_FUSED_EXCHANGE"] = "1"
+            unfused, _ = batched.coherence(trials[lo:hi], 1000., output=output, reduce_group=dist.group.WORLD,
+                                           gather=True, **kw)
+            if rank % 2:
+                del os.environ["SPYB_NO_FUSED_EXCHANGE"]
+            mixed, _ = batched.coherence(trials[lo:hi], 1000., output=output, reduce_group=dist.group.WORLD,
+                                         gather=True, **kw)
+            os.environ.pop("SPYB_NO_FUSED_EXCHANGE", None)
             scale = ref.abs().max().item()
             e_full = (full - ref).abs().max().item() / scale
             f0 = int(np.searchsorted(freqs, fslab[0])) if fslab.size else 0
             e_slab = (slab - ref[:, f0:f0 + slab.shape[1]]).abs().max().item() / scale if fslab.size else 0.0
             e_ar = (allred - ref).abs().max().item() / scale
-            good = e_full <= 2e-6 and e_slab <= 2e-6 and e_ar <= 1e-5 and full.shape == ref.shape
+            e_un = (unfused - ref).abs().max().item() / scale
+            e_mx = (mixed - ref).abs().max().item() / scale
+            good = (e_full <= 2e-6 and e_slab <= 2e-6 and e_ar <= 1e-5 and e_un <= 2e-6 and e_mx <= 2e-6
+                    and full.shape == ref.shape)
             ok = ok and good
-            print(f"[rank {rank}] C={n_chan} {taper} {output}: gathered {e_full:.1e} slab {e_slab:.1e} "
-                  f"all-reduce path {e_ar:.1e} {'ok' if good else 'MISMATCH'}", flush=True)
+            print(f"[rank {rank}] C={n_chan} {taper} {output}: fused exchange gathered {e_full:.1e} slab {e_slab:.1e} "
+                  f"tiles+normalise {e_un:.1e} mixed {e_mx:.1e} all-reduce path {e_ar:.1e} "
+                  f"{'ok' if good else 'MISMATCH'}", flush=True)
     # Granger chain (cfg-4): trial shards, all-reduce of the CSD sum, replicated FP64 factorisation
     trials = synth.ar2_network(16, n_samples=500)
     lo, hi = trial_shard(16, rank, world)

@@ -355,6 +355,8 @@ int mtm_frames(const MtmFramesDesc& d, cudaStream_t stream) {
     // windows (several frames per block) and Bluestein lengths on the Stockham kernel below
     static const bool force_stockham = getenv("SPYB_MTM_STOCKHAM") != nullptr;
     if (!pl->bluestein && !force_stockham) {
+        const int r4 = mtm_launch_4s(pl->log2n, a, stream);
+        if (r4 >= 0) return r4;
         const int rt = mtm_launch_tma(pl->log2n, a, stream);
         if (rt >= 0) return rt;
         const int r8 = mtm_launch_r8(pl->log2n, a, stream);

@@ -34,6 +34,8 @@ struct MtmArgs {
 
 // mtm_dif.cu: returns -1 when the shape is not handled there (the caller then uses the Stockham kernel)
 int mtm_launch_dif(int log2n, const MtmArgs& a, cudaStream_t stream);
+// mtm_4s.cu: four-step kernel (32-channel units, 128-byte lines in and out) for N = 4096, one taper, planar output; -1 when not eligible
+int mtm_launch_4s(int log2n, const MtmArgs& a, cudaStream_t stream);
 // mtm_tma.cu: persistent TMA-pipelined kernel for N = 4096 and full 8-channel tiles; -1 when not eligible
 int mtm_launch_tma(int log2n, const MtmArgs& a, cudaStream_t stream);
 // mtm_r8.cu: 512-point windows (radix-8 passes, frame resident in registers across tapers); -1 when not eligible

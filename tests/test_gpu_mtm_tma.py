@@ -127,30 +127,6 @@ def test_planar_layout_and_trial_stride(engine):
     assert torch.equal(torch.view_as_real(inter)[..., 1], planes[:, :, 1, :])
 
 
-def test_planar_single_taper_rows(engine):
-    """the headline launch shape at a small size: one taper, planar output, 5 trials x 32 channel tiles = 160 work
-    items on 148 SMs (second items exercise the refills) -- Against
-    the oracle per trial and bit for bit against the interleaved output of the same launch shape."""
-    from syncopy_b200 import hostmath as hm
-    trials = synth.white_noise(5, N, 256) + np.float32(0.02)
-    x = torch.from_numpy(trials).to(engine.tdev)
-    tapers = engine.taper_table("hann", N, N, None)
-    scale = hm.mtmfft_scale(N, N)
-    planes = engine.mtmfft(x, tapers, N, scale, polyremoval=0, output="fourier_planar", keeptapers=True,
-                           freq_major=True)
-    assert planes.shape == (N // 2 + 1, 5, 2, 256)
-    got = torch.complex(planes[:, :, 0, :], planes[:, :, 1, :]).cpu().numpy()
-    mk = dict(samplerate=1000., nSamples=None, taper="hann", taper_opt={})
-    foi = np.fft.rfftfreq(N, 1e-3)
-    for t in range(5):
-        want, _ = osp.mtmfft_cF(trials[t].copy(), foi=foi, keeptapers=True, polyremoval=0, output="fourier",
-                                method_kwargs=mk)
-        assert nerr(got[:, t, :], want[0, 0]) <= TOL
-    inter = engine.mtmfft(x, tapers, N, scale, polyremoval=0, output="fourier", keeptapers=True, freq_major=True)
-    assert torch.equal(torch.view_as_real(inter)[..., 0], planes[:, :, 0, :])
-    assert torch.equal(torch.view_as_real(inter)[..., 1], planes[:, :, 1, :])
-
-
 def test_batched_equals_single_trial_bitwise(engine):
     """persistent-loop bookkeeping: trial k of a batch == the same trial run alone, bit for bit"""
     from syncopy_b200 import batched

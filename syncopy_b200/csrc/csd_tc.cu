@@ -532,8 +532,33 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 // the tensor core works on this tile.  Fixed order -> deterministic.
                 const int r0 = (warp & 3) * 32, r_loc = r0 + lane, cb = ((warp - 8) >> 2) * 64;
                 const bool diag_tile = ti == tj;
+                // The rows sit in local HBM; a thread walks 4 chunks x (ranks - 1) sources one round trip after the
+                // other, so each source's four 128-byte pieces are pulled into L2 while the source before it is being
+                // added, and the first source of the NEXT tile while this tile runs (two sources per SM in flight:
+                // a whole tile ahead for every SM would not fit L2 on 8 ranks).
+                auto pf_rows = [&](int src, int pf_f, int pf_t, bool pf_diag) {
+                    const float2* row = a.add_base + (((size_t)src * a.n_freq + pf_f) * a.n_tiles + pf_t) * (128 * 128) +
+                                        (size_t)r_loc * 128 + cb;
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                        if (pf_diag && cb + c0 + 15 < r0) continue;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c0));
+                    }
+                };
+                const int src_first = a.add_skip == 0 ? 1 : 0;
+                if (item == 0 && src_first < a.n_add_src) pf_rows(src_first, f, t, diag_tile);
                 for (int src = 0; src < a.n_add_src; ++src) {
                     if (src == a.add_skip) continue;
+                    {
+                        int nsrc = src + 1;
+                        if (nsrc == a.add_skip) ++nsrc;
+                        if (nsrc < a.n_add_src) pf_rows(nsrc, f, t, diag_tile);
+                        else if (item + 1 < items.count && src_first < a.n_add_src) {
+                            int nf, nti, ntj, nt;
+                            items.decode(item + 1, nf, nti, ntj, nt);
+                            pf_rows(src_first, nf, nt, nti == ntj);
+                        }
+                    }
                     const float4* __restrict__ prow = reinterpret_cast<const float4*>(
                         a.add_base + (((size_t)src * a.n_freq + f) * a.n_tiles + t) * (128 * 128) + (size_t)r_loc * 128 + cb);
 #pragma unroll

@@ -203,6 +203,17 @@ int spyb_cwt(const void* xspec, int n_trials, int n_chan, int n_dft, const void*
 /* batched 2-D transpose of 4- or 8-byte elements: in [batch][rows][cols] -> out [batch][cols][rows] */
 int spyb_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, void* stream);
 
+/*
+ * Transpose with a placement: in [nb1 * nb2][rows][cols] -> out element (b1, b2, col, row) at
+ * b1*stride_b1 + b2*stride_b2 + col*ld_out + row (element units); columns of segment b2 are kept while
+ * b2*cols + col < col_limit.  Lands the time-contiguous rows of a wavelet launch over a range of scales -- or over
+ * overlap-save segments of the trial, the "trials" of that launch being (trial, segment) pairs -- in its slice of
+ * the result [n_trials][n_time][n_scales][n_chan] (transform.py:88-108: one fftconvolve per scale; short kernels do
+ * not need the full padded length).
+ */
+int spyb_transpose_place(const void* in, void* out, int nb1, int nb2, int rows, int cols, int elem_bytes,
+                         long long stride_b1, long long stride_b2, long long ld_out, int col_limit, void* stream);
+
 /* dst[t][i][:] = src[t][idx[i]][:], rows of row_elems float32 (time post-selection, compRoutines.py:593) */
 int spyb_gather_rows(const float* src, int n_trials, long long src_trial_stride, const int* idx, int n_idx,
                      long long row_elems, float* dst, void* stream);

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "spyb_detrend": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _ll, _vp]),
     "spyb_cwt": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "spyb_transpose": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "spyb_transpose_place": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _i, _vp]),
     "spyb_gather_rows": (_i, [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp]),
     "spyb_scale": (_i, [_vp, _ll, _f, _vp]),
     "spyb_sum_trials": (_i, [_vp, _i, _ll, _ll, _f, _f, _vp, _vp]),

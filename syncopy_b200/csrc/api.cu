@@ -209,6 +209,12 @@ int spyb_transpose(const void* in, void* out, int batch, int rows, int cols, int
     return transpose2d(in, out, batch, rows, cols, elem_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int spyb_transpose_place(const void* in, void* out, int nb1, int nb2, int rows, int cols, int elem_bytes,
+                         long long stride_b1, long long stride_b2, long long ld_out, int col_limit, void* stream) {
+    return transpose_place(in, out, nb1, nb2, rows, cols, elem_bytes, stride_b1, stride_b2, ld_out, col_limit,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int spyb_cwt(const void* xspec, int n_trials, int n_chan, int n_dft, const void* kern, const float* expo,
              const int* n_fac, int n_scales, int max_fac, int n_time, int out_kind, int transposed, void* out,
              void* stream) {

@@ -276,6 +276,53 @@ int transpose2d(const void* in, void* out, int batch, int rows, int cols, int el
     return 0;
 }
 
+// Transpose with a placement: in [nb1 * nb2][rows][cols] -> out element (b1, b2, col, row) at
+// b1 * stride_b1 + b2 * stride_b2 + col * ld_out + row, columns of segment b2 kept while b2 * cols + col < col_limit.
+// Lands the time-contiguous rows of a (segmented) wavelet launch in its slice [time][scale range][chan] of the result.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_place_kernel(const T* __restrict__ in, T* __restrict__ out, int nb2, int rows,
+                                                              int cols, long long stride_b1, long long stride_b2,
+                                                              long long ld_out, int col_limit) {
+    __shared__ T tile[32][33];
+    const int b = blockIdx.z, b1 = b / nb2, b2 = b - b1 * nb2;
+    const T* __restrict__ ib = in + (long long)b * rows * cols;
+    T* __restrict__ ob = out + b1 * stride_b1 + b2 * stride_b2;
+    const int keep = min(cols, col_limit - b2 * cols);
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    if (c0 >= keep) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < rows && c < keep) tile[ty + 8 * i][tx] = ib[(long long)r * cols + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (r < rows && c < keep) ob[(long long)c * ld_out + r] = tile[tx][ty + 8 * i];
+    }
+}
+
+int transpose_place(const void* in, void* out, int nb1, int nb2, int rows, int cols, int elem_bytes, long long stride_b1,
+                    long long stride_b2, long long ld_out, int col_limit, cudaStream_t stream) {
+    if (nb1 <= 0 || nb2 <= 0 || rows <= 0 || cols <= 0 || col_limit <= 0) return 0;
+    if (elem_bytes != 4 && elem_bytes != 8) return fail("transpose: element size must be 4 or 8 bytes (got %d)", elem_bytes);
+    const unsigned gy = (unsigned)((rows + 31) / 32);
+    if ((long long)nb1 * nb2 > 65535 || gy > 65535) return fail("transpose: too many batches / rows per launch");
+    if (ld_out < rows) return fail("transpose: output leading dimension %lld < rows %d", ld_out, rows);
+    dim3 grid((cols + 31) / 32, gy, nb1 * nb2);
+    if (elem_bytes == 4)
+        transpose_place_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), static_cast<float*>(out), nb2,
+                                                                rows, cols, stride_b1, stride_b2, ld_out, col_limit);
+    else
+        transpose_place_kernel<float2><<<grid, 256, 0, stream>>>(static_cast<const float2*>(in), static_cast<float2*>(out), nb2,
+                                                                 rows, cols, stride_b1, stride_b2, ld_out, col_limit);
+    SPYB_LAUNCH_CHECK("transpose_place_kernel");
+    count_launch();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // row gather: dst[t][i][:] = src[t][idx[i]][:]   (time post-selection, compRoutines.py:593)
 // ---------------------------------------------------------------------------------------

@@ -79,6 +79,8 @@ struct CwtDesc {
 int cwt_factors(const CwtDesc& d, cudaStream_t stream);
 int cwt_factors_long(const CwtDesc& d, cudaStream_t stream);   // fft_long.cu: circular length > 16384
 int transpose2d(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t stream);
+int transpose_place(const void* in, void* out, int nb1, int nb2, int rows, int cols, int elem_bytes, long long stride_b1,
+                    long long stride_b2, long long ld_out, int col_limit, cudaStream_t stream);
 int detrend(const float* x, int n_trials, long long trial_stride, int n_samples, int n_chan, int polyremoval,
             float* out, long long out_trial_stride, cudaStream_t stream);
 int gather_rows(const float* src, int n_trials, long long src_trial_stride, const int* idx, int n_idx,

@@ -7,6 +7,7 @@ PyTorch CUDA tensors that are handed to libspyb200 as raw device pointers.
 Everything is enqueued on torch's current stream of the device.
 """
 import functools
+import os
 import threading
 from collections import OrderedDict
 
@@ -341,52 +342,92 @@ class Engine:
             if L > MAX_LONG_FFT:
                 raise _lib.SpybError(f"transform of {n_samples} samples needs a circular length of {L} > {MAX_LONG_FFT}")
             nS = len(taps_per_scale)
-            max_fac = max(len(tl) for tl in taps_per_scale)
-            kern = np.zeros((nS, max_fac, L), dtype=np.complex64)
-            expo = np.ones((nS, max_fac), dtype=np.float32)
-            nfac = np.zeros(nS, dtype=np.int32)
-            for si, (tl, el) in enumerate(zip(taps_per_scale, exponents)):
-                nfac[si] = len(tl)
-                for j, (taps, e) in enumerate(zip(tl, el)):
-                    kern[si, j] = hm.conv_same_spectrum(taps, n_samples, L)
-                    expo[si, j] = e
-            return dict(L=L, n_scales=nS, max_fac=max_fac,
-                        kern=torch.from_numpy(kern).to(self.tdev),
-                        expo=torch.from_numpy(expo).to(self.tdev),
-                        nfac=torch.from_numpy(nfac).to(self.tdev),
+            if os.environ.get("SPYB_CWT_NO_SEGMENTS"):
+                groups = [dict(s0=0, s1=nS, L=L, seg=False, V=n_samples, A=0, n_seg=1)]
+            elif os.environ.get("SPYB_CWT_SEG_LENGTHS"):         # experiments: candidate block lengths
+                cand = tuple(int(v) for v in os.environ["SPYB_CWT_SEG_LENGTHS"].split(","))
+                groups = hm.conv_groups(n_samples, taps_per_scale, L, candidates=cand)
+            else:
+                groups = hm.conv_groups(n_samples, taps_per_scale, L)
+            for g in groups:
+                tls, els = taps_per_scale[g["s0"]:g["s1"]], exponents[g["s0"]:g["s1"]]
+                max_fac = max(len(tl) for tl in tls)
+                kern = np.zeros((len(tls), max_fac, g["L"]), dtype=np.complex64)
+                expo = np.ones((len(tls), max_fac), dtype=np.float32)
+                nfac = np.zeros(len(tls), dtype=np.int32)
+                for si, (tl, el) in enumerate(zip(tls, els)):
+                    nfac[si] = len(tl)
+                    for j, (taps, e) in enumerate(zip(tl, el)):
+                        kern[si, j] = (hm.conv_segment_spectrum(taps, g["L"], g["A"]) if g["seg"]
+                                       else hm.conv_same_spectrum(taps, n_samples, g["L"]))
+                        expo[si, j] = e
+                g.update(max_fac=max_fac, kern=torch.from_numpy(kern).to(self.tdev),
+                         expo=torch.from_numpy(expo).to(self.tdev), nfac=torch.from_numpy(nfac).to(self.tdev),
+                         ones=torch.ones((1, g["L"]), dtype=torch.float32, device=self.tdev) if g["seg"] else None)
+            return dict(L=L, n_scales=nS, groups=groups,
                         ones=torch.ones((1, n_samples), dtype=torch.float32, device=self.tdev))
         return self._cached(self._plans, MAX_PLANS, key, make)
 
     def cwt(self, x, plan, output="fourier", out=None):
         """
         x [B, N, C] float32 (already detrended / time-selected) -> [B, N, nScales, C]: per scale the product of
-        powers of 'same' convolutions described by `plan` (see `conv_plan`).
+        powers of 'same' convolutions described by `plan` (see `conv_plan`).  Runs of scales with short kernels go
+        through overlap-save blocks of the trial (`hostmath.conv_groups`), the others through one transform of the
+        full padded length.
         """
         B, N, Cn = x.shape
-        L, nS = plan["L"], plan["n_scales"]
-        xspec = self.mtmfft(x, plan["ones"], L, 1.0, polyremoval=-1, output="fourier", keeptapers=True)
+        nS = plan["n_scales"]
         kind = hm.out_kind(output)
         dt = _CDTYPE[kind == 2]
+        esize = 8 if kind == 2 else 4
         if out is None:
             out = torch.empty((B, N, nS, Cn), dtype=dt, device=self.tdev)
         assert out.is_contiguous() and out.dtype == dt and tuple(out.shape) == (B, N, nS, Cn)
-        if L > self.lib.spyb_max_fft_len(1):
-            # global-memory path (csrc/fft_long.cu): columns = (scale, channel), reference layouts on both sides
-            _lib.check(self.lib.spyb_cwt(xspec.data_ptr(), B, Cn, L, plan["kern"].data_ptr(), plan["expo"].data_ptr(),
-                                         plan["nfac"].data_ptr(), nS, plan["max_fac"], N, kind, 0, out.data_ptr(),
-                                         self.stream()))
-            return out
-        # the transform kernel owns one channel of one scale per block: feed it channel-major spectra and let it
-        # write time-contiguous rows, then transpose into the reference layout [time][scale][channel]
-        nF = L // 2 + 1
-        xs_t = self.scratch("cwt_xspec_t", (B, Cn, nF), torch.complex64)
-        _lib.check(self.lib.spyb_transpose(xspec.data_ptr(), xs_t.data_ptr(), B, nF, Cn, 8, self.stream()))
-        out_t = self.scratch("cwt_out_t" + ("c" if kind == 2 else "f"), (B, nS * Cn, N), dt)
-        _lib.check(self.lib.spyb_cwt(xs_t.data_ptr(), B, Cn, L, plan["kern"].data_ptr(), plan["expo"].data_ptr(),
-                                     plan["nfac"].data_ptr(), nS, plan["max_fac"], N, kind, 1, out_t.data_ptr(),
-                                     self.stream()))
-        _lib.check(self.lib.spyb_transpose(out_t.data_ptr(), out.data_ptr(), B, nS * Cn, N, 8 if kind == 2 else 4,
-                                           self.stream()))
+        smem_max = self.lib.spyb_max_fft_len(1)
+        full_spec = {}                                   # forward spectra of the whole trials, shared by the full-length runs
+
+        def full_spectra(L):
+            if L not in full_spec:
+                full_spec[L] = self.mtmfft(x, plan["ones"], L, 1.0, polyremoval=-1, output="fourier", keeptapers=True)
+            return full_spec[L]
+
+        for g in plan["groups"]:
+            L, nSg, s0 = g["L"], g["s1"] - g["s0"], g["s0"]
+            if not g["seg"] and L > smem_max:
+                # global-memory path (csrc/fft_long.cu): columns = (scale, channel), reference layouts on both sides
+                xspec = full_spectra(L)
+                direct = nSg == nS
+                tmp = out if direct else torch.empty((B, N, nSg, Cn), dtype=dt, device=self.tdev)
+                _lib.check(self.lib.spyb_cwt(xspec.data_ptr(), B, Cn, L, g["kern"].data_ptr(), g["expo"].data_ptr(),
+                                             g["nfac"].data_ptr(), nSg, g["max_fac"], N, kind, 0, tmp.data_ptr(),
+                                             self.stream()))
+                if not direct:
+                    out[:, :, s0:g["s1"]] = tmp
+                continue
+            # the transform kernel owns one channel of one scale per block: feed it channel-major spectra and let it
+            # write time-contiguous rows, then transpose into the slice [time][scales of the run][channel] of the result
+            nF = L // 2 + 1
+            if g["seg"]:
+                n_seg, V = g["n_seg"], g["V"]
+                xspec = self.mtmconvol(x, g["ones"], L, V, -g["A"], n_seg, 1.0, polyremoval=-1, output="fourier",
+                                       keeptapers=True)                      # [B, n_seg, 1, nF, C]
+            else:
+                n_seg, V = 1, N
+                xspec = full_spectra(L)
+            nb = B * n_seg
+            step = max(1, min(B, MAX_LAUNCH_DIM // n_seg))                   # (trial, segment) pairs per launch
+            xs_t = self.scratch("cwt_xspec_t", (nb, Cn, nF), torch.complex64)
+            out_t = self.scratch("cwt_out_t" + ("c" if kind == 2 else "f"), (min(step, B) * n_seg, nSg * Cn, V), dt)
+            for b0 in range(0, B, step):
+                nbb = min(step, B - b0) * n_seg
+                xin = xspec.view(nb, nF, Cn)[b0 * n_seg:]
+                _lib.check(self.lib.spyb_transpose(xin.data_ptr(), xs_t.data_ptr(), nbb, nF, Cn, 8, self.stream()))
+                _lib.check(self.lib.spyb_cwt(xs_t.data_ptr(), nbb, Cn, L, g["kern"].data_ptr(), g["expo"].data_ptr(),
+                                             g["nfac"].data_ptr(), nSg, g["max_fac"], V, kind, 1, out_t.data_ptr(),
+                                             self.stream()))
+                dst = out.data_ptr() + (b0 * N * nS * Cn + s0 * Cn) * esize
+                _lib.check(self.lib.spyb_transpose_place(out_t.data_ptr(), dst, nbb // n_seg, n_seg, nSg * Cn, V, esize,
+                                                         N * nS * Cn, V * nS * Cn, nS * Cn, N, self.stream()))
         return out
 
     def gather_rows(self, src, idx):

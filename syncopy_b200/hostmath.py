@@ -252,6 +252,61 @@ def conv_same_spectrum(taps, n_samples, L):
     return np.fft.fft(h) / L
 
 
+def conv_segment_spectrum(taps, L, shift):
+    """FFT_L(h) / L with h[d mod L] = taps[d + shift + (M-1)//2]: the 'same' convolution of a length-L segment,
+    result index i' = i - shift (overlap-save blocks: the rows a launch keeps start at i' = 0)."""
+    taps = np.asarray(taps, dtype=np.complex128)
+    M = len(taps)
+    assert M <= L
+    j = np.arange(M)
+    h = np.zeros(L, dtype=np.complex128)
+    h[(j - shift - (M - 1) // 2) % L] = taps
+    return np.fft.fft(h) / L
+
+
+def conv_groups(n_samples, taps_per_scale, full_len, smem_max=SMEM_FFT_MAX, candidates=(4096, 8192)):
+    """
+    Split the scales of a 'same'-convolution transform into runs that share a circular length.  A kernel of M taps
+    only needs its own support around every output sample, so short kernels run as overlap-save blocks of length Ls
+    (each block yields V = Ls - (left extent) - (right extent) outputs) instead of one transform of the full padded
+    length: n_seg * Ls log Ls operations instead of full_len log full_len, and smaller shared-memory tiles.
+    Returns a list of dicts {s0, s1, L, seg, V, A, n_seg}: scales [s0, s1), `seg` False = one transform of full_len.
+    Block lengths: measured on B200 at cfg-5 (profiles/cwt_segments_r2.log) 4096 / 8192 pay (superlets -20 %, wavelets
+    unchanged: the transform kernel is not bound by its FFT passes), 1024 / 2048 do not (per-block overheads).
+    """
+    def cost(L, n):                                   # FFT passes + the load / multiply / store work of a transform
+        c = n * L * (np.log2(L) + 6.0)
+        return c * (3.0 if L > smem_max else 1.0)     # beyond the shared-memory kernels the transform lives in HBM
+
+    choice = []
+    for tl in taps_per_scale:
+        left = max(len(t) - 1 - (len(t) - 1) // 2 for t in tl)
+        right = max((len(t) - 1) // 2 for t in tl)
+        best, best_cost = 0, cost(full_len, 1)
+        for Ls in candidates:
+            V = Ls - left - right
+            if Ls >= full_len or V < Ls // 4:
+                continue
+            c = cost(Ls, -(-n_samples // V))
+            if c < 0.85 * best_cost:                  # not worth a separate launch group otherwise
+                best, best_cost = Ls, c
+        choice.append((best, left, right))
+    groups, s0 = [], 0
+    while s0 < len(choice):
+        s1 = s0
+        while s1 < len(choice) and choice[s1][0] == choice[s0][0]:
+            s1 += 1
+        Ls = choice[s0][0]
+        if Ls == 0:
+            groups.append(dict(s0=s0, s1=s1, L=full_len, seg=False, V=n_samples, A=0, n_seg=1))
+        else:
+            A = max(c[1] for c in choice[s0:s1])
+            V = Ls - A - max(c[2] for c in choice[s0:s1])
+            groups.append(dict(s0=s0, s1=s1, L=Ls, seg=True, V=V, A=A, n_seg=-(-n_samples // V)))
+        s0 = s1
+    return groups
+
+
 # ---------------------------------------------------------------------------------------------------------
 # preprocessing: host-side filter design (float64 tables, like the taper tables) for the kernels of csrc/preproc.cu
 # ---------------------------------------------------------------------------------------------------------

@@ -112,3 +112,43 @@ def test_cfg5_shape_subset_vs_oracle(engine):
         want = otf.wavelet_cF(x[k].copy(), slice(None), slice(None), toi=None, polyremoval=0, output="pow",
                               method_kwargs=dict(samplerate=fs, scales=scales, wavelet=wav_o))
         assert nerr(got[k], want) <= TOL
+
+
+@pytest.mark.parametrize("n,c,output", [(3000, 6, "fourier"), (8192, 3, "pow")])
+def test_overlap_save_groups_vs_oracle(engine, n, c, output):
+    """scales whose kernels are short run as overlap-save blocks of the trial, the others through the full padded
+    length (hostmath.conv_groups): one call mixing both, every scale against the oracle"""
+    from syncopy_b200 import compute_functions as cf
+    from syncopy_b200 import hostmath as hm
+    fs = 1000.
+    x = synth.white_noise_trial(n, c, 17) + np.float32(0.3)
+    wav_o, wav_g = otf.Morlet(6), hm.Morlet(6)
+    foi = np.array([2., 5., 9., 20., 60., 150., 300.])
+    scales = wav_o.scale_from_period(1 / foi)
+    kw = dict(toi=None, polyremoval=0, output=output)
+    got = cf.wavelet_cF(x.copy(), slice(None), slice(None),
+                        method_kwargs=dict(samplerate=fs, scales=scales, wavelet=wav_g), **kw)
+    want = otf.wavelet_cF(x.copy(), slice(None), slice(None),
+                          method_kwargs=dict(samplerate=fs, scales=scales, wavelet=wav_o), **kw)
+    assert got.shape == want.shape
+    for s in range(foi.size):
+        assert nerr(got[:, :, s], want[:, :, s]) <= TOL, foi[s]
+    plans = [p for k, p in engine._plans.items() if k[0] == "conv" and k[2] == n]
+    assert plans and any(any(g["seg"] for g in p["groups"]) and any(not g["seg"] for g in p["groups"]) for p in plans)
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_overlap_save_superlet_vs_oracle(engine, adaptive):
+    """superlets: a scale's factors (orders) have different supports; a run of scales takes the largest"""
+    from syncopy_b200 import compute_functions as cf
+    fs, n = 1000., 4000
+    x = synth.white_noise_trial(n, 4, 23)
+    foi = np.array([160., 80., 45., 20.])
+    scales = 1 / (2 * np.pi * foi)
+    mk = dict(samplerate=fs, scales=scales, order_max=6, order_min=1, c_1=3, adaptive=adaptive)
+    for output in ("fourier", "pow"):
+        got = cf.superlet_cF(x.copy(), slice(None), slice(None), polyremoval=0, output=output, method_kwargs=dict(mk))
+        want = otf.superlet_cF(x.copy(), slice(None), slice(None), polyremoval=0, output=output, method_kwargs=dict(mk))
+        assert got.shape == want.shape
+        for k in range(foi.size):
+            assert nerr(got[:, :, k], want[:, :, k]) <= TOL, (output, foi[k])

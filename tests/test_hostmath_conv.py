@@ -98,3 +98,41 @@ def test_conv_same_length_beyond_the_shared_memory_limit():
             p2 *= 2
         assert L <= p2
     assert hm.conv_same_length(20000, [np.zeros(4001)]) == 23040
+
+
+def test_conv_groups_overlap_save_reproduces_fftconvolve_same():
+    """short kernels as overlap-save blocks (hostmath.conv_groups + conv_segment_spectrum), long ones through the
+    full padded length: every scale equals scipy.signal.fftconvolve(x, taps, 'same') (transform.py:88-108)"""
+    import scipy.signal as ss
+    rng = np.random.default_rng(0)
+    n = 3000
+    x = rng.normal(size=n)
+    taps = [[rng.normal(size=m) + 1j * rng.normal(size=m)] for m in (31, 96, 300, 955, 2100, 4000, 7000)]
+    taps[1].append(rng.normal(size=40) + 0j)                       # a scale with two factors of different length
+    L = hm.conv_same_length(n, [t for tl in taps for t in tl])
+    groups = hm.conv_groups(n, taps, L)
+    assert groups[0]["s0"] == 0 and groups[-1]["s1"] == len(taps)
+    assert all(a["s1"] == b["s0"] for a, b in zip(groups, groups[1:]))
+    assert any(g["seg"] for g in groups) and any(not g["seg"] for g in groups)
+    for g in groups:
+        for si in range(g["s0"], g["s1"]):
+            for t in taps[si]:
+                want = ss.fftconvolve(x, t, "same")
+                if g["seg"]:
+                    Ls, V, A = g["L"], g["V"], g["A"]
+                    assert V > 0 and g["n_seg"] * V >= n
+                    K = hm.conv_segment_spectrum(t, Ls, A) * Ls
+                    got = np.zeros(n, complex)
+                    for b in range(g["n_seg"]):
+                        lo = b * V - A
+                        seg = np.zeros(Ls)
+                        a0, a1 = max(lo, 0), min(lo + Ls, n)
+                        seg[a0 - lo:a1 - lo] = x[a0:a1]
+                        y = np.fft.ifft(np.fft.fft(seg) * K)
+                        n1 = min(n, b * V + V)
+                        got[b * V:n1] = y[:n1 - b * V]
+                else:
+                    xp = np.zeros(g["L"])
+                    xp[:n] = x
+                    got = np.fft.ifft(np.fft.fft(xp) * hm.conv_same_spectrum(t, n, g["L"]) * g["L"])[:n]
+                assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()

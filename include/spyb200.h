@@ -218,6 +218,15 @@ int spyb_transpose_place(const void* in, void* out, int nb1, int nb2, int rows, 
 int spyb_gather_rows(const float* src, int n_trials, long long src_trial_stride, const int* idx, int n_idx,
                      long long row_elems, float* dst, void* stream);
 
+/*
+ * In place on complex64 [n_freq][n_chan][n_chan]: lower triangle <- conjugate of the upper one, diagonal made real.
+ * Restores exact Hermitian symmetry of a trial-summed cross-spectral matrix after a reduction over ranks whose
+ * addition order differs between (i, j) and (j, i) (the reference sums trial by trial in one process,
+ * computational_routine.py:1022-1032, so both halves see the same order); wilson_sf.py:104-106 measures the
+ * factorisation error element-wise and never gets below such an asymmetry.
+ */
+int spyb_csd_mirror_upper(void* csd, int n_freq, int n_chan, void* stream);
+
 /* x *= s on n float32 (trial mean `/= nTrials`, computational_routine.py:1030-1032) */
 int spyb_scale(float* x, long long n, float s, void* stream);
 

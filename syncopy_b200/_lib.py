@@ -54,6 +54,7 @@ PROTOTYPES = {
     "spyb_transpose_place": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _i, _vp]),
     "spyb_gather_rows": (_i, [_vp, _i, _ll, _vp, _i, _ll, _vp, _vp]),
     "spyb_scale": (_i, [_vp, _ll, _f, _vp]),
+    "spyb_csd_mirror_upper": (_i, [_vp, _i, _i, _vp]),
     "spyb_sum_trials": (_i, [_vp, _i, _ll, _ll, _f, _f, _vp, _vp]),
     "spyb_axpby": (_i, [_vp, _vp, _f, _f, _vp, _ll, _vp]),
     "spyb_sqdev_accumulate": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),

@@ -225,7 +225,7 @@ def coherence(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper
     n_total = res.n_trials
     if reduce_group is not None:
         from .distributed import allreduce_csd
-        n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group)
+        n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group, engine=eng)
     coh = eng.csd_normalize(res.csd_sum[None], output=output, pre_scale=1.0 / n_total)
     return _finish(coh, to_host, out_host), res.freqs
 
@@ -320,7 +320,7 @@ def granger(trials, samplerate=1, nSamples=None, foi=None, taper="hann", taper_o
     n_total = res.n_trials
     if reduce_group is not None:
         from .distributed import allreduce_csd
-        n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group)
+        n_total = allreduce_csd(res.csd_sum, res.n_trials, reduce_group, engine=eng)
     csd_av = eng.scale_(res.csd_sum, 1.0 / n_total)
     reg, factor, ini_cn = eng.regularize_csd(csd_av, cond_max=cond_max, eps_max=1e-1)
     world = 1

@@ -232,6 +232,10 @@ int spyb_gather_rows(const float* src, int n_trials, long long src_trial_stride,
     return gather_rows(src, n_trials, src_trial_stride, idx, n_idx, row_elems, dst, static_cast<cudaStream_t>(stream));
 }
 
+int spyb_csd_mirror_upper(void* csd, int n_freq, int n_chan, void* stream) {
+    return csd_mirror_upper(csd, n_freq, n_chan, static_cast<cudaStream_t>(stream));
+}
+
 int spyb_scale(float* x, long long n, float s, void* stream) {
     return scale_inplace(x, n, s, static_cast<cudaStream_t>(stream));
 }

@@ -442,6 +442,30 @@ int csd_normalize_tiles(const void* slots, int n_src, int n_freq, int n_chan, fl
 }
 
 // in-place scale of a float buffer (trial mean: computational_routine.py:1030-1032)
+// Lower triangle <- conjugate of the upper one, imaginary part of the diagonal <- 0, in place on [n_freq][C][C]
+// complex64.  A sum of exactly Hermitian partial matrices over ranks is not exactly Hermitian any more when the
+// collective adds the partials of (i, j) and of (j, i) in different orders (ring all-reduce: the order depends on
+// the chunk an element falls into); the Wilson iteration's element-wise error then stalls at that asymmetry.
+__global__ void __launch_bounds__(256) mirror_upper_kernel(float2* __restrict__ csd, int n) {
+    float2* __restrict__ m = csd + (long long)blockIdx.z * n * n;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (i >= n || j >= n || j > i) return;
+    if (j == i) { m[(long long)i * n + i].y = 0.f; return; }
+    const float2 u = m[(long long)j * n + i];
+    m[(long long)i * n + j] = make_float2(u.x, -u.y);
+}
+
+int csd_mirror_upper(void* csd, int n_freq, int n_chan, cudaStream_t stream) {
+    if (n_freq <= 0 || n_chan <= 0) return 0;
+    if (n_freq > 65535) return fail("csd_mirror_upper: too many frequencies per launch (%d)", n_freq);
+    dim3 grid((n_chan + 31) / 32, (n_chan + 7) / 8, n_freq);
+    mirror_upper_kernel<<<grid, 256, 0, stream>>>(static_cast<float2*>(csd), n_chan);
+    SPYB_LAUNCH_CHECK("mirror_upper_kernel");
+    count_launch();
+    return 0;
+}
+
 __global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;

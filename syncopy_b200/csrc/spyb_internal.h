@@ -89,6 +89,7 @@ int gather_rows(const float* src, int n_trials, long long src_trial_stride, cons
 int csd_normalize(const void* csd, long long n_mat, int n_chan, float pre_scale, int out_kind, void* out,
                   cudaStream_t stream);
 int scale_inplace(float* x, long long n, float s, cudaStream_t stream);
+int csd_mirror_upper(void* csd, int n_freq, int n_chan, cudaStream_t stream);
 int sum_trials(const float* src, int n_trials, long long trial_stride, long long n_elems, float alpha, float beta,
                float* acc, cudaStream_t stream);
 

@@ -70,13 +70,17 @@ def trial_shard(n_trials, rank, world):
     return lo, hi
 
 
-def allreduce_csd(csd_sum, n_trials, group=None):
+def allreduce_csd(csd_sum, n_trials, group=None, engine=None):
     """
     In-place SUM all-reduce of a complex64 [nFreq, C, C] partial CSD sum; also reduces the trial
     count.  Returns the global number of trials.
     """
     flat = torch.view_as_real(csd_sum)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if engine is not None and dist.get_world_size(group) > 1:
+        # a ring all-reduce adds the partials of (i, j) and of (j, i) in different orders: exactly Hermitian partial
+        # sums come back Hermitian only to rounding, and the Wilson iteration's element-wise error stalls there
+        engine.csd_mirror_upper(csd_sum)
     cnt = torch.tensor([float(n_trials)], dtype=torch.float64, device=csd_sum.device)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     return int(round(cnt.item()))

@@ -664,6 +664,16 @@ class Engine:
         _lib.check(self.lib.spyb_rectify(x.data_ptr(), out.data_ptr(), x.numel(), self.stream()))
         return out
 
+    def csd_mirror_upper(self, csd):
+        """In place on complex64 [nF, C, C]: lower triangle <- conj(upper), real diagonal (exact Hermitian symmetry
+        after a reduction over ranks)."""
+        assert csd.is_cuda and csd.dtype == torch.complex64 and csd.dim() == 3 and csd.is_contiguous()
+        assert csd.shape[1] == csd.shape[2]
+        for f0 in range(0, csd.shape[0], MAX_LAUNCH_DIM):
+            nf = min(MAX_LAUNCH_DIM, csd.shape[0] - f0)
+            _lib.check(self.lib.spyb_csd_mirror_upper(csd[f0:].data_ptr(), nf, csd.shape[1], self.stream()))
+        return csd
+
     def scale_(self, t, s):
         """In-place t *= s for float32 / complex64 CUDA tensors."""
         assert t.is_cuda and t.is_contiguous()

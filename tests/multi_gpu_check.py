@@ -80,6 +80,17 @@ def main():
     good = e_g <= 1e-3 and bool(meta["converged--bool"]) == bool(meta1["converged--bool"])
     ok = ok and good
     print(f"[rank {rank}] granger (all-reduce path): {e_g:.1e} {'ok' if good else 'MISMATCH'}", flush=True)
+    # the same chain at a size where the all-reduce of the CSD sum runs through several chunks of a ring: partial sums
+    # that are exactly Hermitian must still be so afterwards, or the factorisation's element-wise error stalls
+    # (seen on 4 ranks at the cfg-4 shape: 100 iterations, not converged, before spyb_csd_mirror_upper)
+    torch.manual_seed(100 + rank)
+    xs = torch.randn((40, 4096, 128), device=eng.tdev)           # the cfg-4 shape with fewer trials
+    G, meta, _ = batched.granger(xs, 200., reduce_group=dist.group.WORLD, **kw)
+    good = bool(meta["converged--bool"]) and int(meta["iterations"]) < 60
+    ok = ok and good
+    print(f"[rank {rank}] granger, 128 channels, random shards: {int(meta['iterations'])} iterations, "
+          f"err {float(meta['max rel. err--float']):.1e} {'ok' if good else 'NOT CONVERGED'}", flush=True)
+    del xs
     # sharded Wilson, same CSD on every rank: == the single-rank factorisation to rounding (stage-wise check: the
     # factorisation amplifies differences of the CSD sums, not of its own arithmetic)
     from syncopy_b200.distributed import WilsonExchange

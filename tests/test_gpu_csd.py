@@ -302,3 +302,15 @@ def test_analog_route_equals_spectral_route(engine):
     coh_b = cf.normalize_csd_cF(oc.trial_average(b), "abs")
     assert coh_a.shape == coh_b.shape == (1, 201, 10, 10)
     assert nerr(coh_a, coh_b) <= 1e-5
+
+
+def test_csd_mirror_upper(engine):
+    """spyb_csd_mirror_upper: lower triangle <- conj(upper), real diagonal, upper triangle untouched"""
+    import torch
+    torch.manual_seed(3)
+    for n_freq, n in ((5, 48), (3, 130)):
+        a = torch.randn((n_freq, n, n), dtype=torch.complex64, device=engine.tdev)
+        want = torch.triu(a, 1) + torch.triu(a, 1).conj().transpose(1, 2) + torch.diag_embed(torch.diagonal(a, dim1=1, dim2=2).real).to(a.dtype)
+        got = engine.csd_mirror_upper(a.clone())
+        assert torch.equal(got, want)
+        assert torch.equal(got, got.conj().transpose(1, 2))

@@ -278,7 +278,7 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     uint64_t* acc_full = bars + 3 * TC_STAGES;      // [2]      chain accumulated in TMEM buffer b
     uint64_t* acc_empty = acc_full + 2;             // [2]      epilogue drained TMEM buffer b
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float2* staging = reinterpret_cast<float2*>(acc_empty + 4);   // [8 epilogue warps][32 x 16] transpose buffers
+    float2* staging = reinterpret_cast<float2*>(bars + 16);       // [8 epilogue warps][32 x 16] transpose buffers, 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = a.n_chan;
@@ -559,20 +559,31 @@ csd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                             pf_rows(src_first, nf, nt, nti == ntj);
                         }
                     }
-                    const float4* __restrict__ prow = reinterpret_cast<const float4*>(
-                        a.add_base + (((size_t)src * a.n_freq + f) * a.n_tiles + t) * (128 * 128) + (size_t)r_loc * 128 + cb);
+                    // Coalesced: a warp instruction reads 4 rows x 128 bytes (8 lanes per row piece); the pieces reach
+                    // the row's owner through the warp's 4 KB staging buffer (16-byte slots XOR row: conflict-free both
+                    // ways).  With one row per lane a warp load touched 32 lines and the epilogue, not the tensor
+                    // core, set the pace of the launch.
+                    const float4* __restrict__ pwarp = reinterpret_cast<const float4*>(
+                        a.add_base + (((size_t)src * a.n_freq + f) * a.n_tiles + t) * (128 * 128) + (size_t)r0 * 128 + cb);
+                    float4* stg4 = reinterpret_cast<float4*>(staging + (warp - 8) * (32 * 16));
+                    const int lr = lane >> 3, lq = lane & 7;
 #pragma unroll
                     for (int c0 = 0; c0 < 64; c0 += 16) {
                         // pieces entirely below the diagonal are never written by the producer (nor used here)
                         if (diag_tile && cb + c0 + 15 < r0) continue;
                         float4 v[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = __ldcs(prow + c0 / 2 + q);
+                        for (int it = 0; it < 8; ++it) v[it] = __ldcs(pwarp + (size_t)(4 * it + lr) * 64 + c0 / 2 + lq);
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) stg4[(4 * it + lr) * 8 + (lq ^ ((4 * it + lr) & 7))] = v[it];
+                        __syncwarp();
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            sr[c0 + 2 * q] += v[q].x; si[c0 + 2 * q] += v[q].y;
-                            sr[c0 + 2 * q + 1] += v[q].z; si[c0 + 2 * q + 1] += v[q].w;
+                            const float4 w = stg4[lane * 8 + (q ^ (lane & 7))];
+                            sr[c0 + 2 * q] += w.x; si[c0 + 2 * q] += w.y;
+                            sr[c0 + 2 * q + 1] += w.z; si[c0 + 2 * q + 1] += w.w;
                         }
+                        __syncwarp();
                     }
                 }
             }
@@ -857,7 +868,7 @@ static int launch_tc(const CsdPlanarDesc& d, TcArgs& a, cudaStream_t stream) {
     if (const char* e = getenv("SPYB_TC_BF16")) a.bf16_cross = atoi(e) != 0;
     // 896 bytes of slack reach the next 1024-byte boundary from any 128-byte aligned start (dynamic shared memory
     // starts at least that aligned); 1024 would push the total 104 bytes past the 227 KB limit
-    const size_t smem = 896 + (size_t)TC_STAGES * TC_STAGE + (3 * TC_STAGES + 4 + 2) * 8 + 8 * 32 * 16 * sizeof(float2) +
+    const size_t smem = 896 + (size_t)TC_STAGES * TC_STAGE + 16 * 8 + 8 * 32 * 16 * sizeof(float2) +
                         4 * 128 * sizeof(float);
 
     // per device / context attribute: set on every launch (several engines may live in one process)

@@ -278,6 +278,8 @@ def conv_groups(n_samples, taps_per_scale, full_len, smem_max=SMEM_FFT_MAX, cand
         c = n * L * (np.log2(L) + 6.0)
         return c * (3.0 if L > smem_max else 1.0)     # beyond the shared-memory kernels the transform lives in HBM
 
+    if n_samples <= 0:
+        return [dict(s0=0, s1=len(taps_per_scale), L=full_len, seg=False, V=n_samples, A=0, n_seg=1)]
     choice = []
     for tl in taps_per_scale:
         left = max(len(t) - 1 - (len(t) - 1) // 2 for t in tl)

@@ -160,6 +160,9 @@ int spyb_csd_coherence_planar_slots(const float* planes, long long sx_f, long lo
  */
 int spyb_peer_alloc(long long bytes, void** ptr_out, unsigned char* handle64_out);
 int spyb_peer_open(const unsigned char* handle64, void** ptr_out);
+/* stream-ordered byte fill of local or peer-mapped slot memory (a rank without trials clears its source slots: its
+ * peers add whatever those slots hold) */
+int spyb_peer_memset(void* ptr, int value, long long bytes, void* stream);
 int spyb_peer_close(void* mapped_ptr);
 int spyb_peer_free(void* ptr);
 

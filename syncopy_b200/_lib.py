@@ -45,6 +45,7 @@ PROTOTYPES = {
     "spyb_csd_normalize_tiles": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp]),
     "spyb_peer_alloc": (_i, [_ll, C.POINTER(C.c_void_p), C.c_char_p]),
     "spyb_peer_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "spyb_peer_memset": (_i, [_vp, _i, _ll, _vp]),
     "spyb_peer_close": (_i, [_vp]),
     "spyb_peer_free": (_i, [_vp]),
     "spyb_csd_normalize": (_i, [_vp, _ll, _i, _f, _i, _vp, _vp]),

@@ -156,6 +156,8 @@ def cross_spectra_sum(trials, samplerate=1, nSamples=None, foi=None, taper="hann
             acc = eng.csd_accumulate_planar(view, acc=acc, alpha=1.0 / K, beta=beta)
         else:
             acc = eng.csd_accumulate(view, acc=acc, alpha=1.0 / K, beta=beta, impl=1)
+    if acc is None:                        # no trials on this rank (more ranks than trials): an empty sum
+        acc = torch.zeros((n_freq, n_chan, n_chan), dtype=torch.complex64, device=eng.tdev)
     return CrossSpectraSum(acc, B, freqs)
 
 
@@ -258,6 +260,14 @@ def _coherence_tiles(eng, trials, samplerate, nSamples, foi, taper, taper_opt, p
         return _finish(coh[None], to_host, out_host), freqs
     ex = get_tile_exchange(eng, n_freq, n_chan, reduce_group)
     lo, hi = ex.f_begin[ex.rank], ex.f_begin[ex.rank + 1]
+    if ex.world > 1 and B == 0:
+        # more ranks than trials: this rank has nothing to contract, but its peers add the slots it owns in their
+        # buffers and it still owns a frequency slab -- clear the slots, then sum the peers' tiles of the slab
+        ex.clear_own_source()
+        coh, _ = ex.finish(0, output=output)
+        if not gather:
+            return _finish(coh[None], to_host, out_host), freqs[lo:hi]
+        return _finish(_gather_slabs(eng, ex, coh, reduce_group), to_host, out_host), freqs
     if ex.world > 1 and chunk >= B and not os.environ.get("SPYB_NO_FUSED_EXCHANGE"):
         # several ranks, all rows of the rank in one launch: the exchange is fused into the contraction on both
         # sides (peers' frequencies as tiles over NVLink, barrier, own slab with the peers' tiles added in the

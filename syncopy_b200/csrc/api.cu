@@ -183,6 +183,13 @@ int spyb_peer_open(const unsigned char* handle64, void** ptr_out) {
     return 0;
 }
 
+int spyb_peer_memset(void* ptr, int value, long long bytes, void* stream) {
+    if (!ptr || bytes < 0) return fail("spyb_peer_memset: bad arguments");
+    if (bytes == 0) return 0;
+    SPYB_CUDA(cudaMemsetAsync(ptr, value, (size_t)bytes, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int spyb_peer_close(void* mapped_ptr) {
     SPYB_CUDA(cudaIpcCloseMemHandle(mapped_ptr));
     return 0;

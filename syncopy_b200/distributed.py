@@ -91,6 +91,11 @@ def freq_slabs(n_freq, world):
     return [trial_shard(n_freq, r, world)[0] for r in range(world)] + [n_freq]
 
 
+def _lib_check(rc):
+    from . import _lib
+    _lib.check(rc)
+
+
 class _RawCuda:
     """Zero-copy view of library-owned device memory for torch (`__cuda_array_interface__`)."""
 
@@ -156,6 +161,17 @@ class TileExchange:
         """Contraction of this rank's rows into everyone's slot buffers of the current call."""
         k = self.call % 2
         self.eng.csd_accumulate_tiles(planes, self.owner_ptrs[k], self.f_begin, self.rank, alpha, beta)
+
+    def clear_own_source(self):
+        """A rank without trials contributes zeros: clear the slots it would have filled in every owner's buffer
+        of the current call (its peers add whatever those slots hold)."""
+        k = self.call % 2
+        tile_bytes = self.n_tiles * 128 * 128 * 8
+        for o in range(self.world):
+            nf_o = self.f_begin[o + 1] - self.f_begin[o]
+            if nf_o > 0:
+                _lib_check(self.eng.lib.spyb_peer_memset(int(self.owner_ptrs[k][o]) + self.rank * nf_o * tile_bytes, 0,
+                                                         nf_o * tile_bytes, self.eng.stream()))
 
     def accumulate_others(self, planes):
         """First half of the fused exchange: this rank's rows contracted for every frequency it does NOT own,

@@ -34,6 +34,7 @@ def main():
                                                      (256, 300, 256, "hann", None),      # several accumulation chains
                                                      (384, 11, 256, "hann", None),       # 3 channel blocks, 6 upper tiles
                                                      (160, 7, 256, "hann", None),        # zero-padded last block
+                                                     (128, 1, 256, "hann", None),        # more ranks than trials
                                                      (128, 9, 300, "dpss", {"NW": 2, "Kmax": 3})]:
         trials = synth.white_noise(n_trials, n_samples, n_chan)
         lo, hi = trial_shard(n_trials, rank, world)

@@ -133,10 +133,12 @@ def mtmconvol_cF(trl_dat, soi, postselect, equidistant=True, toi=None, foi=None,
             ext += (-(ext - nperseg) % hop) % nperseg
         n_seg = (ext - noverlap) // hop
         n_frames = max(0, min(n_keep, n_seg))
+        # the taper mean (np.nanmean over the converted per-taper spectra, compRoutines.py:413) runs in the kernel:
+        # K times fewer bytes come back (a NaN sample gives NaN either way)
         spec = eng.mtmconvol(xs, tapers, nperseg, hop, frame_start0, n_frames, hm.stft_scale(nperseg),
-                             polyremoval=pr, freq_idx=f_idx, output=output, keeptapers=True)
-        spec = spec[0].cpu().numpy()                       # [nFrames, K, nF, C]
-        spec = spec[postselect]
+                             polyremoval=pr, freq_idx=f_idx, output=output, keeptapers=bool(keeptapers))
+        spec = spec[0].cpu().numpy()                       # [nFrames, K or 1, nF, C]
+        return spec[postselect]
     else:
         # one window per (non-equidistant) time point: a plain mtmfft of dat[soi[tk]] each
         # (compRoutines.py:392-408; note: no detrending and no padding in this branch)

@@ -136,3 +136,17 @@ def test_conv_groups_overlap_save_reproduces_fftconvolve_same():
                     xp[:n] = x
                     got = np.fft.ifft(np.fft.fft(xp) * hm.conv_same_spectrum(t, n, g["L"]) * g["L"])[:n]
                 assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_conv_groups_edges():
+    """empty time selections and transforms shorter than a block keep the single full-length group; a long trial with
+    one short and one long kernel splits into a block run and a full-length run"""
+    g = hm.conv_groups(0, [[np.ones(5)]], 16)
+    assert len(g) == 1 and not g[0]["seg"] and g[0]["s1"] == 1
+    g = hm.conv_groups(10, [[np.ones(5)]], 16)
+    assert len(g) == 1 and not g[0]["seg"]
+    taps = [[np.ones(31)], [np.ones(20001)]]
+    L = hm.conv_same_length(100000, [t for tl in taps for t in tl])
+    g = hm.conv_groups(100000, taps, L)
+    assert [x["seg"] for x in g] == [True, False] and g[0]["L"] in (4096, 8192) and g[0]["n_seg"] * g[0]["V"] >= 100000
+    assert g[1]["L"] == L

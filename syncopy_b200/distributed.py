@@ -114,6 +114,12 @@ class TileExchange:
     sums the slots of its slab and normalises (`Engine.csd_normalize_tiles`).  Bytes crossing NVLink per rank:
     (world-1)/world * 0.75 * |CSD| instead of 2 (world-1)/world * |CSD| for a ring all-reduce.
 
+    When all rows of a rank fit one launch the exchange is fused into the contraction on both sides
+    (`accumulate_others` / `finish_fused`): the first launch covers the frequencies of the other ranks only, and after
+    the barrier the rank contracts its own slab with the peers' tiles as the starting sums of the normalising
+    epilogue -- no reduction or normalisation kernel.  Both routes store with the same scale, so ranks on different
+    routes (or without trials: `clear_own_source`) stay compatible within one call.
+
     Two buffers alternate between calls: a rank that runs ahead can start filling buffer (k+1) % 2 while a
     slower rank still reads buffer k % 2; passing the barrier of call k+1 implies everyone has finished call k.
     """
